@@ -1,0 +1,62 @@
+"""Seeded synthetic LLaMA-shaped GGML models for parity tests -- TEST INFRASTRUCTURE.
+
+Follows SURVEY.md §8(d): every 2-D weight ~ N(0, 1/K) in f32 then quantized with the reference's
+ggml_quantize_<type> (the call crates/llm-base/src/quantize.rs:365-377 makes, which quantizes every
+".*weight" 2-D tensor including tok_embeddings/output, crates/models/llama/src/lib.rs:390-392);
+norm gains 1 + 0.1 N(0,1) kept f32. Tensor names are the loader's (llama lib.rs:52-91).
+"""
+import numpy as np
+
+from . import bindings as B
+
+CONFIGS = {
+    # tiny shapes the CPU oracle finishes in milliseconds; K multiples of 64 (Q4 row rule, crates/ggml/src/lib.rs:112-118)
+    "tiny":   dict(n_vocab=320, n_embd=256, n_head=4, n_head_kv=4, n_layer=2, n_ff=704, n_rot=64, n_ctx=128),
+    "small":  dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=8, n_layer=3, n_ff=1408, n_rot=64, n_ctx=256),
+    # 7B layer geometry with few layers (BASELINE.json configs[1]/[2] shapes)
+    "7b-2l":  dict(n_vocab=32000, n_embd=4096, n_head=32, n_head_kv=32, n_layer=2, n_ff=11008, n_rot=128, n_ctx=1024),
+    "7b":     dict(n_vocab=32000, n_embd=4096, n_head=32, n_head_kv=32, n_layer=32, n_ff=11008, n_rot=128, n_ctx=2048),
+    "13b":    dict(n_vocab=32000, n_embd=5120, n_head=40, n_head_kv=40, n_layer=40, n_ff=13824, n_rot=128, n_ctx=2048),
+}
+
+
+def tensor_shapes(hp):
+    """name -> (ne1 rows N, ne0 cols K) for 2-D weights, (n,) for 1-D."""
+    e, f, v = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
+    gqa = e // (hp["n_head"] // hp["n_head_kv"])
+    shapes = {"tok_embeddings.weight": (v, e), "norm.weight": (e,), "output.weight": (v, e)}
+    for i in range(hp["n_layer"]):
+        p = f"layers.{i}."
+        shapes[p + "attention_norm.weight"] = (e,)
+        shapes[p + "attention.wq.weight"] = (e, e)
+        shapes[p + "attention.wk.weight"] = (gqa, e)
+        shapes[p + "attention.wv.weight"] = (gqa, e)
+        shapes[p + "attention.wo.weight"] = (e, e)
+        shapes[p + "ffn_norm.weight"] = (e,)
+        shapes[p + "feed_forward.w1.weight"] = (f, e)
+        shapes[p + "feed_forward.w2.weight"] = (e, f)
+        shapes[p + "feed_forward.w3.weight"] = (f, e)
+    return shapes
+
+
+def make_llama(hp, wtype, quantize, seed=0x5EED0000, gain=1.0):
+    """Returns (hp_with_wtype, {name: ndarray}) -- uint8 block rows for 2-D weights, f32 for norms.
+
+    `quantize(type, f32[N,K]) -> uint8[N, row_bytes]` is the reference quantizer (RefLib.quantize) or
+    its restatement (Oracle.quantize); tests assert the two agree bit for bit.
+    """
+    hp = dict(hp, wtype=wtype)
+    out = {}
+    for idx, (name, shp) in enumerate(tensor_shapes(hp).items()):
+        rng = np.random.default_rng(seed + idx)
+        if len(shp) == 1:
+            out[name] = (1.0 + 0.1 * rng.standard_normal(shp)).astype(np.float32)
+        else:
+            n, k = shp
+            w = (rng.standard_normal((n, k)) * (gain / np.sqrt(k))).astype(np.float32)
+            out[name] = quantize(wtype, w)
+    return hp, out
+
+
+def make_tokens(hp, n, seed=0x70CE11):
+    return np.random.default_rng(seed).integers(0, hp["n_vocab"], size=n, dtype=np.int32)
