@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- LLaMA-7B Q4_0 tokens/sec on B200 (BASELINE.json metric), decode@1 headline + prefill@512 beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (N>1: launched by torchrun, one replica per GPU)
+  python bench.py --impl reference [...]                        the reference's own ggml CPU path on the host cores
+
+A "step" is one pass of the hot path over one batch: one decode token (Llama::evaluate with 1 token) at n_past = 512 on a
+synthetic, device-generated LLaMA-7B Q4_0 model (BASELINE.json configs[1]).  `value` is measured with inputs resident in
+HBM (token id and logits stay on the device); `e2e` goes through the host-buffer call (b200_session_evaluate: token H2D,
+logits D2H, sync) every step.  Timing: CUDA events on the backend's stream, W >= 3 warm-up steps, the 3.7 GB of weights
+are far larger than the 126 MB L2 so every step streams them from HBM.  Multi-GPU (the path does not need to shard: 7B fits
+one GPU) = N independent replicas, no data-path collective, "scaling": "weak".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HP_7B = dict(n_vocab=32000, n_embd=4096, n_head=32, n_head_kv=32, n_layer=32, n_rot=128, n_ff=11008, wtype=2)
+N_PAST = 512
+METRIC = "LLaMA-7B Q4_0 tokens/sec (decode@1, n_past=512)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"], bf16_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def algorithmic_bytes_per_token(hp, n_past, blk=18):
+    """every weight byte once + the f16 KV cache read + one embedding row."""
+    e, f, v, nl = hp["n_embd"], hp["n_ff"], hp["n_vocab"], hp["n_layer"]
+    gqa = e // (hp["n_head"] // hp["n_head_kv"])
+    per_layer = (e * e * 2 + 2 * gqa * e + 3 * e * f) // 32 * blk
+    weights = nl * per_layer + v * e // 32 * blk
+    kv = 2 * nl * (n_past + 1) * gqa * 2
+    return weights, kv, e // 32 * blk
+
+
+def prefill_flops(hp, n):
+    e, f, v, nl = hp["n_embd"], hp["n_ff"], hp["n_vocab"], hp["n_layer"]
+    gqa = e // (hp["n_head"] // hp["n_head_kv"])
+    return 2.0 * n * (nl * (e * e * 2 + 2 * gqa * e + 3 * e * f) + v * e)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own ggml.c (oracle/_ref, else the plain-C port) on the host cores
+# --------------------------------------------------------------------------------------------------------------------------------
+def cpu_reference_decode(steps, warmup, sample_layers=2, log=lambda *a: None):
+    """Bounded sample of the same workload: a LLaMA-7B-geometry Q4_0 model with `sample_layers` transformer layers (+ the full
+    32000 x 4096 lm_head) decoded at n_past = 512 on the host cores; the 32-layer token time is
+    t_head + 32 * (t_sample - t_head) / sample_layers, with t_head timed as the lm_head mat-vec alone."""
+    from oracle import bindings as B
+    from oracle import synth
+    kind = "reference" if B.have_ref("ref") else "port"
+    nproc = os.cpu_count() or 1
+    hp = dict(synth.CONFIGS["7b"], n_layer=sample_layers, n_ctx=N_PAST + 64)
+    t0 = time.time()
+    if kind == "reference":
+        ref = B.RefLib("ref")
+        quant = ref.quantize
+    else:
+        orc = B.Oracle()
+        quant = orc.quantize
+    hp, tens = synth.make_llama(hp, B.Q4_0, quant)
+    log(f"cpu: synthetic {sample_layers}-layer 7B-geometry model built in {time.time() - t0:.1f}s")
+    toks = synth.make_tokens(hp, N_PAST + 1)
+    best = None
+    cands = sorted({max(1, nproc // 2), nproc, min(8, nproc)}) if kind == "reference" else [nproc]
+    for nt in cands:
+        if kind == "reference":
+            m = ref.llama(hp, tens, n_threads=nt, n_batch=N_PAST)
+        else:
+            os.environ["OMP_NUM_THREADS"] = str(nt)
+            m = orc.llama(hp, tens)
+        t0 = time.time()
+        m.eval(toks[:N_PAST])                     # fill the KV cache (CPU prefill of the sample)
+        t_prefill = time.time() - t0
+        ts = []
+        for i in range(warmup + steps):          # n_past walks 512, 513, ... (the harness has no rewind); n_ctx leaves room for 64 steps
+            t0 = time.time()
+            m.eval(toks[N_PAST:N_PAST + 1])
+            ts.append(time.time() - t0)
+        t_sample = statistics.median(ts[warmup:])
+        # embedding + final norm + lm_head alone: the same model with zero transformer layers
+        hp0 = dict(hp, n_layer=0)
+        tens0 = {k: v for k, v in tens.items() if not k.startswith("layers.")}
+        m0 = ref.llama(hp0, tens0, n_threads=nt, n_batch=8) if kind == "reference" else orc.llama(hp0, tens0)
+        th = []
+        for i in range(warmup + steps):
+            t0 = time.time()
+            m0.eval(toks[N_PAST:N_PAST + 1])
+            th.append(time.time() - t0)
+        m0.close()
+        t_head = min(statistics.median(th[warmup:]), t_sample * 0.95)
+        t_tok = t_head + 32 * (t_sample - t_head) / sample_layers
+        log(f"cpu[{kind}] threads={nt}: sample step {t_sample * 1e3:.1f} ms, lm_head {t_head * 1e3:.1f} ms -> 32-layer token {t_tok * 1e3:.1f} ms; sample prefill@512 {t_prefill:.1f}s")
+        if best is None or t_tok < best["t_tok"]:
+            best = dict(t_tok=t_tok, threads=nt, t_sample=t_sample, t_head=t_head, t_prefill_sample=t_prefill)
+        m.close()
+    return dict(value=1.0 / best["t_tok"], unit="tokens/s", cores=best["threads"], kind=kind,
+                sample=f"{sample_layers}-layer LLaMA-7B-geometry Q4_0 model + full lm_head, decode at n_past~{N_PAST}, median of {steps} steps; "
+                       f"token time = t_head + 32*(t_sample - t_head)/{sample_layers} (t_sample {best['t_sample'] * 1e3:.1f} ms, t_head {best['t_head'] * 1e3:.1f} ms); host has {nproc} logical cores",
+                ms_per_step=best["t_tok"] * 1e3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true")
+    ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is NOT the benchmark config")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = args.steps, max(3, args.warmup)
+    log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rsteps = min(steps, 12)
+        cb = cpu_reference_decode(rsteps, min(warmup, 3), log=log)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": rsteps,
+                "warmup": min(warmup, 3), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8xint8->f32 (Q4_0 x Q8_0 blocks)", "data": "synthetic",
+                "config": {"workload": "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1]), reference ggml CPU path", "l2": "n/a (CPU)"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- our arm ----------------------------------------------------------------------------------------------------
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import llm_b200
+    from llm_b200 import _lib
+    L = _lib.lib()
+    hp = dict(HP_7B, n_layer=args.layers)
+    t0 = time.time()
+    model = llm_b200.Llama(hp, llm_b200.ModelParameters(context_size=2048), device=local_rank)
+    model.synthesize(0x5EED0000 + rank)
+    log(f"model synthesized on device in {time.time() - t0:.1f}s; weight bytes streamed per token = {model.weight_bytes}")
+    sess = model.start_session(llm_b200.InferenceSessionConfig(n_batch=512))
+    rng = np.random.default_rng(0x70CE11 + rank)
+    prompt = rng.integers(0, hp["n_vocab"], N_PAST + 1, dtype=np.int32)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        sess.sync()
+
+    # prefill@512 (also fills the KV cache for the decode steps)
+    prefill = None
+    reps = 1 if args.no_prefill else 5
+    pf_ms = []
+    for r in range(reps + 1):
+        sess.rewind(0)
+        tok = np.ascontiguousarray(prompt[:N_PAST])
+        L.b200_timing_begin()
+        rc = L.b200_session_evaluate(sess._s, tok.ctypes.data, N_PAST, None, 0)
+        ms = L.b200_timing_end_ms()
+        assert rc == 0, rc
+        if r > 0 or reps == 1:
+            pf_ms.append(ms)
+    pf_launches = sess.last_launches
+    if not args.no_prefill:
+        ms = statistics.median(pf_ms)
+        fl = prefill_flops(hp, N_PAST)
+        pk = peaks()
+        prefill = {"value": N_PAST / (ms * 1e-3), "unit": "tokens/s", "ms": ms, "reps": reps, "launches": pf_launches,
+                   "tensor_frac_of_bf16_sustained": fl / (ms * 1e-3) / (pk["bf16_sustained"] * 1e12),
+                   "note": "integer-exact (conformant) path: int8 MMA per quant block + fp32 scale-accumulate; includes attention and the 2 KB token upload"}
+        log(f"prefill@512: {ms:.2f} ms -> {prefill['value']:.0f} tok/s ({pf_launches} kernels)")
+
+    # decode@1 at n_past = 512: device-resident arm
+    one = np.ascontiguousarray(prompt[N_PAST:N_PAST + 1])
+    assert L.b200_session_evaluate(sess._s, one.ctypes.data, 1, None, 0) == 0      # leaves the token id in HBM
+    launches_per_step = sess.last_launches
+    for _ in range(warmup):
+        sess.rewind(N_PAST)
+        assert L.b200_session_evaluate_device(sess._s, None, 1) == 0
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        L.b200_timing_begin()
+        for _ in range(steps):
+            sess.rewind(N_PAST)
+            L.b200_session_evaluate_device(sess._s, None, 1)
+        ms_dev = L.b200_timing_end_ms()
+        barrier()
+        # e2e arm: host token in, host logits out, every step
+        logits = np.empty(hp["n_vocab"], np.float32)
+        for _ in range(3):
+            sess.rewind(N_PAST)
+            L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0)
+        barrier()
+        t0 = time.perf_counter()
+        L.b200_timing_begin()
+        for _ in range(steps):
+            sess.rewind(N_PAST)
+            L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0)
+        ms_e2e = L.b200_timing_end_ms()
+        wall_e2e = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(ms_e2e, wall_e2e)             # the host-visible time is what a caller experiences
+        barrier()
+        # roofline probe of the dominant kernel (quantized mat-vec) on the real weights
+        nl, nbytes = C.c_int64(0), C.c_double(0)
+        probe_reps = 3
+        ms_probe = L.b200_session_probe_matvec(sess._s, probe_reps, C.byref(nl), C.byref(nbytes))
+    clocks = clk.summary()
+    assert np.isfinite(logits).all()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    wbytes, kvbytes, embbytes = algorithmic_bytes_per_token(hp, N_PAST)
+    tok_bytes = wbytes + kvbytes + embbytes
+    value = world * steps / (ms_dev * 1e-3)
+    e2e = world * steps / (ms_e2e * 1e-3)
+    probe_gbs = nbytes.value / (ms_probe * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8xint8->f32 (Q4_0 x Q8_0 blocks)", "data": "synthetic",
+        "config": {"workload": "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1])", "n_layer": hp["n_layer"], "n_ctx": 2048,
+                   "kv_cache": "f16", "parallelism": f"{world} independent replica(s), no collective",
+                   "l2": "inputs larger than L2: 3.7 GB of weights streamed per step vs 126 MB L2",
+                   "weights": "random-init, generated on device (N(0,1/K) -> Q4_0 by the reference's quantizer rule)"},
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 * hp["n_vocab"], "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches_per_step * steps,
+        "launches_per_step": launches_per_step,
+        "roofline": {"bound": "hbm", "kernel": "mmvq_kernel<Q4_0> (all 129 weight mat-vecs of the model, timed alone)",
+                     "achieved": probe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": probe_gbs / pk["hbm_gbs"], "peak_source": pk["source"] + " (burst copy)",
+                     "traffic": None, "launches": int(nl.value), "avg_launch_us": ms_probe * 1e3 / max(1, nl.value),
+                     "algorithmic_bytes_per_launch": nbytes.value / max(1, nl.value)},
+        "step_roofline": {"bytes_per_token": tok_bytes, "weights": wbytes, "kv": kvbytes, "achieved_gbs": tok_bytes / (ms_dev / steps * 1e-3) / 1e9,
+                          "frac": tok_bytes / (ms_dev / steps * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "clocks": clocks,
+    }
+    if prefill:
+        line["prefill"] = prefill
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cb = cpu_reference_decode(6, 2, log=log)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:                                       # the baseline leg must never take the GPU number down
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+/*
+ * include/llm_b200.h -- native host runtime of libllm_b200.so: the reference's model/session interface for the
+ * LLaMA graph, as a C ABI (the reference's own host layer is Rust; no Rust toolchain exists here, so the same interface
+ * is offered to C / ctypes callers -- see INTEGRATION.md for the Rust `extern "C"` block that binds it).
+ *
+ * Names, argument meaning and error behaviour mirror:
+ *   Hyperparameters                 crates/models/llama/src/lib.rs:403-447
+ *   ModelParameters                 crates/llm-base/src/model/mod.rs:197-229   (context_size, rope overrides)
+ *   KnownModel::new / TensorLoader  crates/models/llama/src/lib.rs:43-140      (tensor names "layers.N.attention.wq.weight", ...)
+ *   KnownModel::start_session       crates/models/llama/src/lib.rs:130-141  -> InferenceSession::new (inference_session.rs:114-217)
+ *   InferenceSessionConfig          crates/llm-base/src/inference_session.rs:799-841 (n_batch; KV cache is f16)
+ *   Model::evaluate + OutputRequest crates/models/llama/src/lib.rs:144-368, crates/llm-base/src/model/common.rs:6-39
+ *   InferenceSession::feed_prompt   crates/llm-base/src/inference_session.rs:299-350 (chunks of n_batch, ContextFull)
+ *
+ * Where the per-node seam (ggml_b200.h) replays the reference's graph one node per call, this front end owns the whole
+ * forward pass: a static schedule of fused sm_100a kernels (captured as a CUDA graph for decode), weights and KV cache
+ * resident in HBM.  Both front ends run the same kernels and are held to the same parity bar.
+ */
+#ifndef LLM_B200_H
+#define LLM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_model b200_model;
+typedef struct b200_session b200_session;
+
+typedef struct {
+    int32_t n_vocab, n_embd, n_head, n_head_kv, n_layer, n_rot, n_ff;
+    int32_t wtype;            /* enum ggml_type of the 2-D weights: 2 Q4_0, 3 Q4_1, 6 Q5_0, 7 Q5_1, 8 Q8_0 */
+    int32_t context_size;     /* ModelParameters::context_size (default 2048) */
+    float   rope_freq_base;   /* RoPEOverrides::frequency_base (10000) */
+    float   rope_freq_scale;  /* RoPEOverrides::frequency_scale (1) */
+} b200_llama_hparams;
+
+typedef struct {
+    int32_t n_batch;          /* InferenceSessionConfig::n_batch: largest evaluate() batch; reference default 8, prefill@512 uses 512 */
+    int32_t flags;            /* B200_SESSION_* */
+} b200_session_config;
+
+enum {
+    B200_SESSION_NO_GRAPH = 1,     /* do not capture decode steps as CUDA graphs (debug) */
+    B200_SESSION_UNFUSED  = 2,     /* one kernel per reference graph node (the seam's kernels) instead of the fused schedule */
+};
+
+enum {                            /* return codes (0 = ok).  CUDA failures print and exit(1) like the reference backend. */
+    B200_OK = 0,
+    B200_ERR_CONTEXT_FULL = -1,   /* InferenceError::ContextFull (inference_session.rs:311-313, 388-390) */
+    B200_ERR_BAD_ARG = -2,
+    B200_ERR_UNKNOWN_TENSOR = -3, /* LoadError::UnknownTensor */
+    B200_ERR_TENSOR_SHAPE = -4,   /* LoadError::TensorWrongSize */
+    B200_ERR_NOT_LOADED = -5,
+};
+
+int  b200_init(int device);                                   /* accelerator::initialize(device), accelerator/mod.rs:68-77 */
+int  b200_device_info(int32_t *sm_count, size_t *free_bytes, size_t *total_bytes);
+
+b200_model *b200_llama_new(const b200_llama_hparams *hp);
+/* TensorLoader::load(name) + Tensor::transfer_to(Backend::Gpu): host bytes in GGML layout (block arrays for quantized types) */
+int  b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const void *host_data, size_t nbytes);
+/* fill every tensor with seeded synthetic weights generated ON the device (N(0,1/K) -> the reference's quantizer rule);
+ * used by bench.py / smoke: there are no model files in this environment */
+int  b200_model_synthesize(b200_model *m, uint64_t seed);
+/* copy a tensor back in GGML layout (tests; lets the CPU oracle run on device-generated weights) */
+int  b200_model_read_tensor(b200_model *m, const char *name, void *host_out, size_t nbytes);
+size_t b200_model_tensor_nbytes(b200_model *m, const char *name);
+size_t b200_model_weight_bytes(b200_model *m);                /* bytes of all 2-D weights resident in HBM */
+void b200_model_free(b200_model *m);
+
+b200_session *b200_model_start_session(b200_model *m, const b200_session_config *cfg);
+/* One forward pass over `n` tokens appended at n_past (InferenceSession::compute + Llama::evaluate).  tokens: HOST int32.
+ * logits_out: HOST f32, n rows of n_vocab when all_logits (OutputRequest::all_logits), else the last row (read_last_token).
+ * May be NULL (feed only).  n must be <= n_batch. */
+int  b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, float *logits_out, int32_t all_logits);
+/* feed_prompt: evaluate in chunks of n_batch; last row of logits returned */
+int  b200_session_feed_prompt(b200_session *s, const int32_t *tokens, int32_t n, float *last_logits_out);
+/* Device-resident variant for measurements: tokens already in HBM, logits stay in HBM (no host copies, no sync) */
+int  b200_session_evaluate_device(b200_session *s, const int32_t *d_tokens, int32_t n);
+const float *b200_session_device_logits(b200_session *s);    /* [n][n_vocab] of the last evaluate */
+int32_t b200_session_n_past(const b200_session *s);
+int  b200_session_set_n_past(b200_session *s, int32_t n_past);   /* rewind (supports_rewind, llama lib.rs:396-398) */
+/* raw f16 KV cache bytes (get_snapshot, inference_session.rs:599-646): which = 0 memory_k, 1 memory_v */
+int  b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t nbytes);
+int  b200_session_sync(b200_session *s);
+/* kernels launched by the last evaluate (for bench.py's gpu_launches) and whether it replayed a CUDA graph */
+int32_t b200_session_last_launches(const b200_session *s);
+void b200_session_free(b200_session *s);
+
+/* stream handle (cudaStream_t) on which everything above is ordered -- for CUDA-event timing from the host side */
+void *b200_stream(void);
+/* CUDA-event stopwatch on that stream: begin records an event; end records a second one, waits for it and returns ms */
+int   b200_timing_begin(void);
+float b200_timing_end_ms(void);
+/* Roofline probe for the dominant decode kernel: `reps` passes over EVERY weight mat-vec of the model (wqkv, wo, w13, w2 per
+ * layer + output; 3.7 GB for 7B Q4_0, far larger than L2) on the session's current quantized activations, timed with CUDA
+ * events.  Returns total ms; *launches = kernels launched, *bytes = algorithmic weight bytes streamed (all reps). */
+float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches, double *bytes);
+
+/* ---- single-op entry points on HOST buffers (unit tests, INTEGRATION examples).  Each uploads, runs the kernel, downloads. */
+int  b200_op_quantize_act(int32_t vec_dot_type, const float *x, int64_t K, int64_t B, int8_t *qs_out, float *d_out, float *aux_out);
+int  b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, const float *x, int64_t B, float *dst, int32_t impl);
+enum { B200_MM_AUTO = 0, B200_MM_VEC = 1, B200_MM_SIMPLE = 2, B200_MM_TENSOR = 3 };
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,69 @@
+"""Loader of the C-ABI product library (llm_b200/libllm_b200.so).
+
+There is no Python/NumPy/CPU implementation of anything in this package: if the CUDA library is missing or no CUDA device
+is present, calls fail loudly (ImportError here, exit(1) inside the library -- the reference backend's error behaviour,
+LC/ggml-cuda.cu:24-53)."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libllm_b200.so")
+
+_lib = None
+
+
+class LlamaHparams(C.Structure):
+    """b200_llama_hparams (include/llm_b200.h) <- Hyperparameters, crates/models/llama/src/lib.rs:403-447."""
+    _fields_ = [("n_vocab", C.c_int32), ("n_embd", C.c_int32), ("n_head", C.c_int32), ("n_head_kv", C.c_int32),
+                ("n_layer", C.c_int32), ("n_rot", C.c_int32), ("n_ff", C.c_int32), ("wtype", C.c_int32),
+                ("context_size", C.c_int32), ("rope_freq_base", C.c_float), ("rope_freq_scale", C.c_float)]
+
+
+class SessionConfig(C.Structure):
+    """b200_session_config <- InferenceSessionConfig, crates/llm-base/src/inference_session.rs:799-841."""
+    _fields_ = [("n_batch", C.c_int32), ("flags", C.c_int32)]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). llm_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    L.b200_init.argtypes = [C.c_int]
+    L.b200_device_info.argtypes = [C.POINTER(i32), C.POINTER(sz), C.POINTER(sz)]
+    L.b200_stream.restype = vp
+    L.b200_llama_new.restype = vp
+    L.b200_llama_new.argtypes = [C.POINTER(LlamaHparams)]
+    L.b200_model_load_tensor.argtypes = [vp, C.c_char_p, i32, vp, sz]
+    L.b200_model_synthesize.argtypes = [vp, C.c_uint64]
+    L.b200_model_read_tensor.argtypes = [vp, C.c_char_p, vp, sz]
+    L.b200_model_tensor_nbytes.restype = sz
+    L.b200_model_tensor_nbytes.argtypes = [vp, C.c_char_p]
+    L.b200_model_weight_bytes.restype = sz
+    L.b200_model_weight_bytes.argtypes = [vp]
+    L.b200_model_free.argtypes = [vp]
+    L.b200_model_start_session.restype = vp
+    L.b200_model_start_session.argtypes = [vp, C.POINTER(SessionConfig)]
+    L.b200_session_evaluate.argtypes = [vp, vp, i32, vp, i32]
+    L.b200_session_feed_prompt.argtypes = [vp, vp, i32, vp]
+    L.b200_session_evaluate_device.argtypes = [vp, vp, i32]
+    L.b200_session_device_logits.restype = vp
+    L.b200_session_device_logits.argtypes = [vp]
+    L.b200_session_n_past.argtypes = [vp]
+    L.b200_session_set_n_past.argtypes = [vp, i32]
+    L.b200_session_read_kv.argtypes = [vp, i32, vp, sz]
+    L.b200_session_sync.argtypes = [vp]
+    L.b200_session_last_launches.argtypes = [vp]
+    L.b200_session_free.argtypes = [vp]
+    L.b200_timing_begin.argtypes = []
+    L.b200_timing_end_ms.restype = C.c_float
+    L.b200_session_probe_matvec.restype = C.c_float
+    L.b200_session_probe_matvec.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(C.c_double)]
+    L.b200_op_quantize_act.argtypes = [i32, vp, i64, i64, vp, vp, vp]
+    L.b200_op_mul_mat.argtypes = [i32, vp, i64, i64, vp, i64, vp, i32]
+    _lib = L
+    return L

@@ -1,0 +1,500 @@
+// llm_b200/csrc/session.cu -- native host runtime (include/llm_b200.h): Llama model + InferenceSession on the B200.
+//
+// Mirrors, in C++ over the kernels of this directory, what the reference does in Rust over ggml:
+//   Llama::new / TensorLoader          crates/models/llama/src/lib.rs:43-140
+//   InferenceSession::new / compute    crates/llm-base/src/inference_session.rs:114-295
+//   Llama::evaluate (the graph)        crates/models/llama/src/lib.rs:144-368
+// The forward pass below is that graph, node for node in arithmetic, but scheduled statically: no per-eval graph
+// construction, no arena reset, weights resident in HBM in the planes layout, wq|wk|wv and w1|w3 stored as single matrices
+// so one activation quantization and one mat-mul launch serve them.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/llm_b200.h"
+#include "kernels.cuh"
+#include "runtime.h"
+
+namespace b200 {
+void synth_qweight(const QWeight &w, uint64_t seed, cudaStream_t st);
+void synth_gain(float *g, int64_t n, uint64_t seed, cudaStream_t st);
+}  // namespace b200
+using namespace b200;
+
+namespace {
+
+QWeight row_view(const QWeight &w, int64_t row0, int64_t nrows) {   // rows [row0, row0+nrows) of a planes matrix
+    QWeight v = w;
+    v.N = nrows;
+    v.qs = w.qs + (size_t)row0 * w.nb * qs_bytes(w.type);
+    if (w.qh) v.qh = w.qh + (size_t)row0 * w.nb;
+    v.dm = (const uint8_t *)w.dm + (size_t)row0 * w.nb * (has_min(w.type) ? 4 : 2);
+    v.base = nullptr;
+    return v;
+}
+
+struct Layer {
+    float *attention_norm = nullptr, *ffn_norm = nullptr;
+    QWeight wqkv, wo, w13, w2;          // wqkv rows: [wq | wk | wv]; w13 rows: [w1 | w3]
+};
+
+}  // namespace
+
+struct b200_model {
+    b200_llama_hparams hp;
+    int gqa = 0, hd = 0;
+    char *slab = nullptr;               // one HBM allocation for every weight
+    size_t slab_bytes = 0, weight_bytes = 0;
+    QWeight wte, output;
+    float *norm = nullptr;
+    std::vector<Layer> layers;
+    std::vector<uint8_t> loaded;        // per tensor slot
+    int n_loaded = 0;
+
+    struct Slot { QWeight q; float *f = nullptr; int64_t n = 0; bool is_q = false; };
+    bool lookup(const char *name, Slot &s, int &slot_id);
+    int n_slots() const { return 3 + 9 * hp.n_layer; }
+};
+
+struct b200_session {
+    b200_model *m = nullptr;
+    b200_session_config cfg;
+    int n_past = 0;
+    __half *memory_k = nullptr, *memory_v = nullptr;     // [n_layer][n_ctx][gqa] and [n_layer][gqa][n_ctx] (V transposed)
+    // activations (sized for n_batch rows)
+    int32_t *d_tokens = nullptr;
+    float *x = nullptr, *cur = nullptr, *ff = nullptr, *qkv = nullptr, *kq = nullptr, *h13 = nullptr, *hmul = nullptr, *logits = nullptr;
+    int8_t *xq = nullptr; float2 *xds = nullptr;
+    // pinned host staging
+    int32_t *h_tokens = nullptr; float *h_logits = nullptr;
+    int last_launches = 0;
+    int last_n = 0;
+};
+
+bool b200_model::lookup(const char *name, Slot &s, int &slot_id) {
+    const int e = hp.n_embd, f = hp.n_ff;
+    s = Slot();
+    if (!strcmp(name, "tok_embeddings.weight")) { s.q = wte; s.is_q = true; slot_id = 0; return true; }
+    if (!strcmp(name, "norm.weight")) { s.f = norm; s.n = e; slot_id = 1; return true; }
+    if (!strcmp(name, "output.weight")) { s.q = output; s.is_q = true; slot_id = 2; return true; }
+    int il = -1; char sub[64];
+    if (sscanf(name, "layers.%d.%63s", &il, sub) != 2 || il < 0 || il >= hp.n_layer) return false;
+    Layer &L = layers[il];
+    const int base = 3 + 9 * il;
+    if (!strcmp(sub, "attention_norm.weight")) { s.f = L.attention_norm; s.n = e; slot_id = base + 0; return true; }
+    if (!strcmp(sub, "ffn_norm.weight"))       { s.f = L.ffn_norm; s.n = e; slot_id = base + 1; return true; }
+    s.is_q = true;
+    if (!strcmp(sub, "attention.wq.weight")) { s.q = row_view(L.wqkv, 0, e); slot_id = base + 2; return true; }
+    if (!strcmp(sub, "attention.wk.weight")) { s.q = row_view(L.wqkv, e, gqa); slot_id = base + 3; return true; }
+    if (!strcmp(sub, "attention.wv.weight")) { s.q = row_view(L.wqkv, e + gqa, gqa); slot_id = base + 4; return true; }
+    if (!strcmp(sub, "attention.wo.weight")) { s.q = L.wo; slot_id = base + 5; return true; }
+    if (!strcmp(sub, "feed_forward.w1.weight")) { s.q = row_view(L.w13, 0, f); slot_id = base + 6; return true; }
+    if (!strcmp(sub, "feed_forward.w3.weight")) { s.q = row_view(L.w13, f, f); slot_id = base + 7; return true; }
+    if (!strcmp(sub, "feed_forward.w2.weight")) { s.q = L.w2; slot_id = base + 8; return true; }
+    return false;
+}
+
+namespace {
+
+// ---- the forward pass (crates/models/llama/src/lib.rs:166-362) ---------------------------------------------------------------
+struct Launches { int n = 0; };
+}  // namespace
+void silu_mul_rows(const float *h13, float *out, int64_t f, int64_t n, cudaStream_t st);
+namespace {
+
+void mm(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda,
+        cudaStream_t st, Launches &L) {
+    if (B == 1)      mul_mat_vec_q(w, xq, xds, dst, addend, st);
+    else if (B < 16) mul_mat_q_simple(w, xq, xds, dst, ldd, B, addend, lda, st);
+    else             mul_mat_q(w, xq, xds, dst, ldd, B, addend, lda, st);
+    L.n++;
+}
+
+void forward(b200_session *s, int n) {
+    b200_model *m = s->m;
+    const b200_llama_hparams &hp = m->hp;
+    cudaStream_t st = rt().stream;
+    const int e = hp.n_embd, f = hp.n_ff, hd = m->hd, gqa = m->gqa, n_head = hp.n_head, n_head_kv = hp.n_head_kv;
+    const int n_ctx = hp.context_size, n_past = s->n_past, n_kv = n_past + n;
+    const int vdt = vec_dot_type(hp.wtype);
+    const int qkv_ld = e + 2 * gqa;
+    const float kq_scale = 1.0f / sqrtf((float)e / (float)n_head);                           // llama lib.rs:268-270
+    const RopeTable &rope = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, hd, n_ctx);
+    Launches L;
+
+    get_rows_q(m->wte, s->d_tokens, s->x, n, st); L.n++;                                      // :170
+    for (int il = 0; il < hp.n_layer; il++) {
+        const Layer &ly = m->layers[il];
+        __half *Kl = s->memory_k + (size_t)il * n_ctx * gqa;                                  // :227-231
+        __half *Vl = s->memory_v + (size_t)il * n_ctx * gqa;                                  // :233-239
+        rms_norm(s->x, s->cur, ly.attention_norm, e, n, 5e-6f, st); L.n++;                    // :183,186
+        quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
+        mm(ly.wqkv, s->xq, s->xds, s->qkv, qkv_ld, n, nullptr, 0, st, L);                     // :194,208,223
+        // RoPE on Q and K heads in place: [hd, n_head + n_head_kv, n] with row stride qkv_ld    :190-217
+        rope_f32(s->qkv, s->qkv, hd, n_head + n_head_kv, n, hd, qkv_ld, hd, qkv_ld, n_past, rope, st); L.n++;
+        {   // store K (row per position) and V (transposed) into the f16 cache                   :243-244
+            StridedDesc sk{{gqa, n, 1, 1}, {4, (int64_t)qkv_ld * 4, 0, 0}}, dk{{gqa, n, 1, 1}, {2, (int64_t)gqa * 2, 0, 0}};
+            cpy_strided(s->qkv + e, T_F32, sk, Kl + (size_t)n_past * gqa, T_F16, dk, st); L.n++;
+            StridedDesc sv{{n, gqa, 1, 1}, {(int64_t)qkv_ld * 4, 4, 0, 0}}, dv{{n, gqa, 1, 1}, {2, (int64_t)n_ctx * 2, 0, 0}};
+            cpy_strided(s->qkv + e + gqa, T_F32, sv, Vl + n_past, T_F16, dv, st); L.n++;
+        }
+        // KQ[h][i][j] = K[j][h] . f16(Q[i][h])                                                    :246-265
+        mul_mat_f16(Kl, hd, n_kv, n_head_kv, (int64_t)gqa * 2, (int64_t)hd * 2,
+                    s->qkv, n, n_head, (int64_t)qkv_ld * 4, (int64_t)hd * 4,
+                    s->kq, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4, st); L.n++;
+        soft_max(s->kq, s->kq, n_kv, (int64_t)n_head * n, n, kq_scale, true, n_past, true, true, st); L.n++;   // :268-281
+        // KQV[h][i][c] = V[h][c][:] . f16(P[h][i][:]) written straight into the merged [n][e] layout     :284-307
+        mul_mat_f16(Vl, n_kv, hd, n_head_kv, (int64_t)n_ctx * 2, (int64_t)n_ctx * hd * 2,
+                    s->kq, n, n_head, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4,
+                    s->cur, (int64_t)e * 4, (int64_t)hd * 4, st); L.n++;
+        quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
+        mm(ly.wo, s->xq, s->xds, s->ff, e, n, s->x, e, st, L);                                // :310,314  (inpFF = wo.cur + inpSA)
+        rms_norm(s->ff, s->cur, ly.ffn_norm, e, n, 5e-6f, st); L.n++;                         // :318,321
+        quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
+        mm(ly.w13, s->xq, s->xds, s->h13, 2 * f, n, nullptr, 0, st, L);                       // :323,325
+        silu_mul_rows(s->h13, s->hmul, f, n, st); L.n++;                                      // :328,330  silu(w1 x) * (w3 x)
+        quantize_act(vdt, s->hmul, f, s->xq, s->xds, f, n, st); L.n++;
+        mm(ly.w2, s->xq, s->xds, s->x, e, n, s->ff, e, st, L);                                // :332,334
+    }
+    rms_norm(s->x, s->cur, m->norm, e, n, 5e-6f, st); L.n++;                                  // :343,346
+    quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
+    mm(m->output, s->xq, s->xds, s->logits, hp.n_vocab, n, nullptr, 0, st, L);                // :352
+    s->last_launches = L.n;
+    s->last_n = n;
+    s->n_past += n;                                                                           // inference_session.rs:288
+}
+
+}  // namespace
+
+// silu(a)*b over rows laid out [a(f) | b(f)]
+__global__ void silu_mul_rows_kernel(const uint16_t *__restrict__ t, const float *__restrict__ h13, float *__restrict__ out, int64_t f, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t r = i / f, c = i - r * f;
+    const float a = h13[r * 2 * f + c], b = h13[r * 2 * f + f + c];
+    out[i] = __fmul_rn(f16_bits_to_f32(__ldg(t + f32_to_f16_bits(a))), b);
+}
+void silu_mul_rows(const float *h13, float *out, int64_t f, int64_t n, cudaStream_t st) {
+    const int64_t total = f * n;
+    if (total == 0) return;
+    silu_mul_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(luts().silu, h13, out, f, total);
+    B200_CHECK(cudaGetLastError());
+}
+
+// ==== exported C ABI ==========================================================================================================
+extern "C" {
+
+int b200_init(int device) {
+    Runtime &R = rt();
+    if (!R.inited) R.device = device;
+    R.ensure_init();
+    return R.device == device ? B200_OK : B200_ERR_BAD_ARG;
+}
+
+int b200_device_info(int32_t *sm_count, size_t *free_bytes, size_t *total_bytes) {
+    rt().ensure_init();
+    if (sm_count) *sm_count = rt().sm_count;
+    size_t fr = 0, tot = 0;
+    B200_CHECK(cudaMemGetInfo(&fr, &tot));
+    if (free_bytes) *free_bytes = fr;
+    if (total_bytes) *total_bytes = tot;
+    return B200_OK;
+}
+
+void *b200_stream(void) { rt().ensure_init(); return (void *)rt().stream; }
+
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+int b200_timing_begin(void) {
+    rt().ensure_init();
+    if (!g_ev0) { B200_CHECK(cudaEventCreate(&g_ev0)); B200_CHECK(cudaEventCreate(&g_ev1)); }
+    B200_CHECK(cudaEventRecord(g_ev0, rt().stream));
+    return B200_OK;
+}
+float b200_timing_end_ms(void) {
+    B200_CHECK(cudaEventRecord(g_ev1, rt().stream));
+    B200_CHECK(cudaEventSynchronize(g_ev1));
+    float ms = 0.f;
+    B200_CHECK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+    return ms;
+}
+
+float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches, double *bytes) {
+    if (!s || reps < 1) return -1.f;
+    b200_model *m = s->m;
+    cudaStream_t st = rt().stream;
+    const int e = m->hp.n_embd, f = m->hp.n_ff;
+    // a valid quantized activation row for both K = n_embd and K = n_ff
+    B200_CHECK(cudaMemsetAsync(s->hmul, 0, (size_t)f * 4, st));
+    quantize_act(vec_dot_type(m->hp.wtype), s->hmul, f, s->xq, s->xds, f, 1, st);
+    (void)e;
+    int64_t n = 0;
+    auto pass = [&]() {
+        for (auto &L : m->layers) {
+            mul_mat_vec_q(L.wqkv, s->xq, s->xds, s->qkv, nullptr, st);
+            mul_mat_vec_q(L.wo, s->xq, s->xds, s->ff, nullptr, st);
+            mul_mat_vec_q(L.w13, s->xq, s->xds, s->h13, nullptr, st);
+            mul_mat_vec_q(L.w2, s->xq, s->xds, s->cur, nullptr, st);
+            n += 4;
+        }
+        mul_mat_vec_q(m->output, s->xq, s->xds, s->logits, nullptr, st);
+        n += 1;
+    };
+    pass();                      // warm-up (also first-touch of every page)
+    n = 0;
+    b200_timing_begin();
+    for (int r = 0; r < reps; r++) pass();
+    const float ms = b200_timing_end_ms();
+    if (launches) *launches = n;
+    if (bytes) *bytes = (double)m->weight_bytes * reps;
+    return ms;
+}
+
+b200_model *b200_llama_new(const b200_llama_hparams *hp) {
+    if (!hp || !is_quant(hp->wtype) || hp->n_embd % 64 || hp->n_ff % 64 || hp->n_head <= 0 || hp->n_head_kv <= 0 ||
+        hp->n_head % hp->n_head_kv || hp->n_embd % hp->n_head || hp->n_layer <= 0 || hp->context_size <= 0) return nullptr;
+    rt().ensure_init();
+    b200_model *m = new b200_model();
+    m->hp = *hp;
+    if (m->hp.rope_freq_base == 0.f) m->hp.rope_freq_base = 10000.0f;
+    if (m->hp.rope_freq_scale == 0.f) m->hp.rope_freq_scale = 1.0f;
+    const int e = hp->n_embd, f = hp->n_ff, v = hp->n_vocab, t = hp->wtype;
+    m->hd = e / hp->n_head;
+    m->gqa = e / (hp->n_head / hp->n_head_kv);
+    m->layers.resize(hp->n_layer);
+    // pass 1: sizes, pass 2: carve
+    for (int pass = 0; pass < 2; pass++) {
+        size_t off = 0;
+        auto carve_q = [&](QWeight &w, int64_t K, int64_t N) {
+            const size_t b = qweight_layout(w, t, K, N, pass ? m->slab + off : nullptr);
+            off += b;
+            if (pass) m->weight_bytes += (size_t)N * (K / QK) * ggml_block_bytes(t);
+        };
+        auto carve_f = [&](float *&p, int64_t n) { if (pass) p = (float *)(m->slab + off); off += ((size_t)n * 4 + 255) & ~(size_t)255; };
+        carve_q(m->wte, e, v); carve_q(m->output, e, v); carve_f(m->norm, e);
+        for (auto &L : m->layers) {
+            carve_f(L.attention_norm, e); carve_f(L.ffn_norm, e);
+            carve_q(L.wqkv, e, e + 2 * m->gqa); carve_q(L.wo, e, e); carve_q(L.w13, e, 2 * f); carve_q(L.w2, f, e);
+        }
+        if (!pass) { m->slab_bytes = off; B200_CHECK(cudaMalloc(&m->slab, off)); }
+    }
+    m->weight_bytes -= (size_t)v * (e / QK) * ggml_block_bytes(t);   // tok_embeddings is only gathered from, never streamed
+    m->loaded.assign(m->n_slots(), 0);
+    return m;
+}
+
+size_t b200_model_weight_bytes(b200_model *m) { return m ? m->weight_bytes : 0; }
+
+size_t b200_model_tensor_nbytes(b200_model *m, const char *name) {
+    b200_model::Slot s; int id;
+    if (!m || !m->lookup(name, s, id)) return 0;
+    return s.is_q ? (size_t)s.q.N * s.q.nb * ggml_block_bytes(s.q.type) : (size_t)s.n * 4;
+}
+
+int b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const void *host_data, size_t nbytes) {
+    if (!m || !name || !host_data) return B200_ERR_BAD_ARG;
+    b200_model::Slot s; int id;
+    if (!m->lookup(name, s, id)) return B200_ERR_UNKNOWN_TENSOR;
+    Runtime &R = rt();
+    if (s.is_q) {
+        if (type != s.q.type || nbytes != (size_t)s.q.N * s.q.nb * ggml_block_bytes(type)) return B200_ERR_TENSOR_SHAPE;
+        R.op_arena.reset();
+        void *raw = R.op_arena.get(nbytes, R.stream);
+        B200_CHECK(cudaMemcpyAsync(raw, host_data, nbytes, cudaMemcpyHostToDevice, R.stream));
+        repack_weights(s.q, raw, R.stream);
+        B200_CHECK(cudaStreamSynchronize(R.stream));
+    } else {
+        if (type != T_F32 || nbytes != (size_t)s.n * 4) return B200_ERR_TENSOR_SHAPE;
+        B200_CHECK(cudaMemcpy(s.f, host_data, nbytes, cudaMemcpyHostToDevice));
+    }
+    if (!m->loaded[id]) { m->loaded[id] = 1; m->n_loaded++; }
+    return B200_OK;
+}
+
+int b200_model_read_tensor(b200_model *m, const char *name, void *host_out, size_t nbytes) {
+    if (!m || !name || !host_out) return B200_ERR_BAD_ARG;
+    b200_model::Slot s; int id;
+    if (!m->lookup(name, s, id)) return B200_ERR_UNKNOWN_TENSOR;
+    Runtime &R = rt();
+    if (s.is_q) {
+        if (nbytes != (size_t)s.q.N * s.q.nb * ggml_block_bytes(s.q.type)) return B200_ERR_TENSOR_SHAPE;
+        R.op_arena.reset();
+        void *raw = R.op_arena.get(nbytes, R.stream);
+        unpack_weights(s.q, raw, R.stream);
+        B200_CHECK(cudaMemcpyAsync(host_out, raw, nbytes, cudaMemcpyDeviceToHost, R.stream));
+        B200_CHECK(cudaStreamSynchronize(R.stream));
+    } else {
+        if (nbytes != (size_t)s.n * 4) return B200_ERR_TENSOR_SHAPE;
+        B200_CHECK(cudaStreamSynchronize(R.stream));
+        B200_CHECK(cudaMemcpy(host_out, s.f, nbytes, cudaMemcpyDeviceToHost));
+    }
+    return B200_OK;
+}
+
+int b200_model_synthesize(b200_model *m, uint64_t seed) {
+    if (!m) return B200_ERR_BAD_ARG;
+    cudaStream_t st = rt().stream;
+    uint64_t id = 0;
+    auto q = [&](const QWeight &w) { synth_qweight(w, seed + 0x1000003ull * (++id), st); };
+    auto g = [&](float *p, int64_t n) { synth_gain(p, n, seed + 0x1000003ull * (++id), st); };
+    q(m->wte); g(m->norm, m->hp.n_embd); q(m->output);
+    for (auto &L : m->layers) { g(L.attention_norm, m->hp.n_embd); g(L.ffn_norm, m->hp.n_embd); q(L.wqkv); q(L.wo); q(L.w13); q(L.w2); }
+    B200_CHECK(cudaStreamSynchronize(st));
+    m->loaded.assign(m->n_slots(), 1);
+    m->n_loaded = m->n_slots();
+    return B200_OK;
+}
+
+void b200_model_free(b200_model *m) {
+    if (!m) return;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    if (m->slab) B200_CHECK(cudaFree(m->slab));
+    delete m;
+}
+
+b200_session *b200_model_start_session(b200_model *m, const b200_session_config *cfg) {
+    if (!m || !cfg || cfg->n_batch < 1) return nullptr;
+    if (m->n_loaded != m->n_slots()) { fprintf(stderr, "llm_b200: start_session: %d of %d tensors loaded\n", m->n_loaded, m->n_slots()); return nullptr; }
+    b200_session *s = new b200_session();
+    s->m = m; s->cfg = *cfg;
+    const b200_llama_hparams &hp = m->hp;
+    const size_t e = hp.n_embd, f = hp.n_ff, B = cfg->n_batch, n_ctx = hp.context_size, gqa = m->gqa;
+    const size_t kv_elems = (size_t)hp.n_layer * n_ctx * gqa;
+    B200_CHECK(cudaMalloc(&s->memory_k, kv_elems * 2));
+    B200_CHECK(cudaMalloc(&s->memory_v, kv_elems * 2));
+    B200_CHECK(cudaMemset(s->memory_k, 0, kv_elems * 2));           // offload_no_scratch zero-fills (LC/ggml-cuda.cu:3967-3973)
+    B200_CHECK(cudaMemset(s->memory_v, 0, kv_elems * 2));
+    const size_t kmax = e > f ? e : f;
+    B200_CHECK(cudaMalloc(&s->d_tokens, B * 4));
+    B200_CHECK(cudaMalloc(&s->x, B * e * 4));
+    B200_CHECK(cudaMalloc(&s->cur, B * e * 4));
+    B200_CHECK(cudaMalloc(&s->ff, B * e * 4));
+    B200_CHECK(cudaMalloc(&s->qkv, B * (e + 2 * gqa) * 4));
+    B200_CHECK(cudaMalloc(&s->kq, (size_t)hp.n_head * B * n_ctx * 4));
+    B200_CHECK(cudaMalloc(&s->h13, B * 2 * f * 4));
+    B200_CHECK(cudaMalloc(&s->hmul, B * f * 4));
+    B200_CHECK(cudaMalloc(&s->logits, B * (size_t)hp.n_vocab * 4));
+    B200_CHECK(cudaMalloc(&s->xq, B * kmax));
+    B200_CHECK(cudaMalloc(&s->xds, B * (kmax / QK) * sizeof(float2)));
+    B200_CHECK(cudaMallocHost(&s->h_tokens, B * 4));
+    B200_CHECK(cudaMallocHost(&s->h_logits, B * (size_t)hp.n_vocab * 4));
+    rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
+    return s;
+}
+
+int32_t b200_session_n_past(const b200_session *s) { return s ? s->n_past : -1; }
+int b200_session_set_n_past(b200_session *s, int32_t n_past) {
+    if (!s || n_past < 0 || n_past > s->n_past) return B200_ERR_BAD_ARG;
+    s->n_past = n_past;
+    return B200_OK;
+}
+int32_t b200_session_last_launches(const b200_session *s) { return s ? s->last_launches : 0; }
+
+int b200_session_evaluate_device(b200_session *s, const int32_t *d_tokens, int32_t n) {
+    if (!s || n < 1 || n > s->cfg.n_batch) return B200_ERR_BAD_ARG;
+    if (s->n_past + n > s->m->hp.context_size) return B200_ERR_CONTEXT_FULL;
+    if (d_tokens && d_tokens != s->d_tokens)
+        B200_CHECK(cudaMemcpyAsync(s->d_tokens, d_tokens, (size_t)n * 4, cudaMemcpyDeviceToDevice, rt().stream));
+    forward(s, n);
+    return B200_OK;
+}
+const float *b200_session_device_logits(b200_session *s) { return s ? s->logits : nullptr; }
+
+int b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, float *logits_out, int32_t all_logits) {
+    if (!s || !tokens || n < 1 || n > s->cfg.n_batch) return B200_ERR_BAD_ARG;
+    if (s->n_past + n > s->m->hp.context_size) return B200_ERR_CONTEXT_FULL;
+    for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= s->m->hp.n_vocab) return B200_ERR_BAD_ARG;
+    cudaStream_t st = rt().stream;
+    memcpy(s->h_tokens, tokens, (size_t)n * 4);
+    B200_CHECK(cudaMemcpyAsync(s->d_tokens, s->h_tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    forward(s, n);
+    const size_t V = s->m->hp.n_vocab;
+    if (logits_out) {
+        const size_t rows = all_logits ? n : 1;
+        const float *src = all_logits ? s->logits : s->logits + (size_t)(n - 1) * V;
+        B200_CHECK(cudaMemcpyAsync(s->h_logits, src, rows * V * 4, cudaMemcpyDeviceToHost, st));
+        B200_CHECK(cudaStreamSynchronize(st));
+        memcpy(logits_out, s->h_logits, rows * V * 4);
+    }
+    return B200_OK;
+}
+
+int b200_session_feed_prompt(b200_session *s, const int32_t *tokens, int32_t n, float *last_logits_out) {
+    if (!s || !tokens || n < 0) return B200_ERR_BAD_ARG;
+    if (s->n_past + n > s->m->hp.context_size) return B200_ERR_CONTEXT_FULL;          // inference_session.rs:311-313
+    for (int i = 0; i < n; i += s->cfg.n_batch) {                                     // :315-316 chunks(n_batch)
+        const int c = (n - i) < s->cfg.n_batch ? (n - i) : s->cfg.n_batch;
+        const bool last = i + c >= n;
+        const int rc = b200_session_evaluate(s, tokens + i, c, last ? last_logits_out : nullptr, 0);
+        if (rc != B200_OK) return rc;
+    }
+    return B200_OK;
+}
+
+int b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t nbytes) {
+    if (!s || !host_out) return B200_ERR_BAD_ARG;
+    const size_t kv_bytes = (size_t)s->m->hp.n_layer * s->m->hp.context_size * s->m->gqa * 2;
+    if (nbytes != kv_bytes) return B200_ERR_TENSOR_SHAPE;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    B200_CHECK(cudaMemcpy(host_out, which ? s->memory_v : s->memory_k, kv_bytes, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchronize(rt().stream)); return B200_OK; }
+
+void b200_session_free(b200_session *s) {
+    if (!s) return;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    void *dev[] = {s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds};
+    for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
+    if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
+    if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));
+    delete s;
+}
+
+// ---- single-op entry points on host buffers ---------------------------------------------------------------------------------
+int b200_op_quantize_act(int32_t vdt, const float *x, int64_t K, int64_t B, int8_t *qs_out, float *d_out, float *aux_out) {
+    if (!x || K % QK || (vdt != T_Q8_0 && vdt != T_Q8_1)) return B200_ERR_BAD_ARG;
+    Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
+    cudaStream_t st = R.stream;
+    const size_t nblk = (size_t)B * (K / QK);
+    float *dx = (float *)R.op_arena.get((size_t)B * K * 4, st);
+    int8_t *dq = (int8_t *)R.op_arena.get((size_t)B * K, st);
+    float2 *dds = (float2 *)R.op_arena.get(nblk * sizeof(float2), st);
+    B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
+    quantize_act(vdt, dx, K, dq, dds, K, B, st);
+    std::vector<float2> h(nblk);
+    B200_CHECK(cudaMemcpyAsync(qs_out, dq, (size_t)B * K, cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(h.data(), dds, nblk * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < nblk; i++) { if (d_out) d_out[i] = h[i].x; if (aux_out) aux_out[i] = h[i].y; }
+    return B200_OK;
+}
+
+int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, const float *x, int64_t B, float *dst, int32_t impl) {
+    if (!is_quant(wtype) || !w_ggml || !x || !dst || K % 64) return B200_ERR_BAD_ARG;
+    Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
+    cudaStream_t st = R.stream;
+    const size_t raw_bytes = (size_t)N * (K / QK) * ggml_block_bytes(wtype);
+    void *raw = R.op_arena.get(raw_bytes, st);
+    B200_CHECK(cudaMemcpyAsync(raw, w_ggml, raw_bytes, cudaMemcpyHostToDevice, st));
+    QWeight w;
+    const size_t pb = qweight_layout(w, wtype, K, N, nullptr);
+    qweight_layout(w, wtype, K, N, R.op_arena.get(pb, st));
+    repack_weights(w, raw, st);
+    float *dx = (float *)R.op_arena.get((size_t)B * K * 4, st);
+    float *dd = (float *)R.op_arena.get((size_t)B * N * 4, st);
+    int8_t *xq = (int8_t *)R.op_arena.get((size_t)B * K, st);
+    float2 *xds = (float2 *)R.op_arena.get((size_t)B * (K / QK) * sizeof(float2), st);
+    B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
+    quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
+    if (impl == B200_MM_AUTO) impl = B == 1 ? B200_MM_VEC : (B < 16 ? B200_MM_SIMPLE : B200_MM_TENSOR);
+    if (impl == B200_MM_VEC) { for (int64_t b = 0; b < B; b++) mul_mat_vec_q(w, xq + b * K, xds + b * (K / QK), dd + b * N, nullptr, st); }
+    else if (impl == B200_MM_SIMPLE) mul_mat_q_simple(w, xq, xds, dd, N, B, nullptr, 0, st);
+    else mul_mat_q(w, xq, xds, dd, N, B, nullptr, 0, st);
+    B200_CHECK(cudaMemcpyAsync(dst, dd, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+}  // extern "C"
