@@ -44,6 +44,9 @@ typedef struct {
 enum {
     B200_SESSION_NO_GRAPH = 1,     /* do not capture decode steps as CUDA graphs (debug) */
     B200_SESSION_UNFUSED  = 2,     /* one kernel per reference graph node (the seam's kernels) instead of the fused schedule */
+    B200_SESSION_FAST     = 4,     /* order-free kernels: integer-exact block dots but a different f32 summation order than the
+                                      reference's AVX2 build.  NOT conformant: the reference graph amplifies 1e-7 differences to ~1e-2
+                                      in the logits (DESIGN.md "chaos").  Default (flag clear) = bit-exact kernels. */
 };
 
 enum {                            /* return codes (0 = ok).  CUDA failures print and exit(1) like the reference backend. */
@@ -85,6 +88,11 @@ int  b200_session_set_n_past(b200_session *s, int32_t n_past);   /* rewind (supp
 /* raw f16 KV cache bytes (get_snapshot, inference_session.rs:599-646): which = 0 memory_k, 1 memory_v */
 int  b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t nbytes);
 int  b200_session_sync(b200_session *s);
+/* debug taps for parity work: keep a copy of one intermediate buffer of (layer, stage) during the next evaluate.
+ * stages: 1 attn-norm out [n][e], 2 qkv before rope [n][e+2gqa], 3 qkv after rope, 4 KQ raw [h][n][n_kv], 5 KQ softmax, 6 merged
+ * KQV [n][e], 7 inpFF, 8 ffn-norm out, 9 [w1x | w3x] [n][2f], 10 silu*mul [n][f], 11 layer output [n][e] */
+int  b200_session_set_tap(b200_session *s, int32_t layer, int32_t stage);
+int64_t b200_session_read_tap(b200_session *s, float *host_out, int64_t max_count);
 /* kernels launched by the last evaluate (for bench.py's gpu_launches) and whether it replayed a CUDA graph */
 int32_t b200_session_last_launches(const b200_session *s);
 void b200_session_free(b200_session *s);
@@ -102,7 +110,7 @@ float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches
 /* ---- single-op entry points on HOST buffers (unit tests, INTEGRATION examples).  Each uploads, runs the kernel, downloads. */
 int  b200_op_quantize_act(int32_t vec_dot_type, const float *x, int64_t K, int64_t B, int8_t *qs_out, float *d_out, float *aux_out);
 int  b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, const float *x, int64_t B, float *dst, int32_t impl);
-enum { B200_MM_AUTO = 0, B200_MM_VEC = 1, B200_MM_SIMPLE = 2, B200_MM_TENSOR = 3 };
+enum { B200_MM_AUTO = 0, B200_MM_VEC = 1, B200_MM_SIMPLE = 2, B200_MM_TENSOR = 3, B200_MM_EXACT = 4 };   /* AUTO = EXACT */
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,10 @@ void mul_mat_q(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst
 // cross-check implementation (CUDA cores, dp4a), same contract
 void mul_mat_q_simple(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 
+// ---- exact.cu : bit-exact (AVX2 operation order) versions; the DEFAULT of both front ends -----------------------------------------
+// same contract as mul_mat_q for any B >= 1; results are bit-identical to ggml_compute_forward_mul_mat on the reference's x86 build
+void mul_mat_q_exact(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
+
 // ---- rowops.cu : warp/block-reduce kernels ------------------------------------------------------------------------
 struct Luts { const uint16_t *silu, *gelu, *exp; };   // 3 x 64 Ki fp16 tables built on the host with libm (LC/ggml.c:4313-4326)
 const Luts &luts();                                   // uploaded on first use
@@ -66,5 +70,10 @@ void cpy_strided(const void *src, int src_type, const StridedDesc &s, void *dst,
 void mul_mat_f16(const __half *src0, int64_t ne00, int64_t ne01, int64_t ne02, int64_t nb01, int64_t nb02,
                  const float *src1, int64_t ne11, int64_t ne12, int64_t nb11, int64_t nb12,
                  float *dst, int64_t nbd1, int64_t nbd2, cudaStream_t st);
+
+// ggml_vec_dot_f16 operation order (exact.cu); causal_past >= 0 skips outputs i0 > causal_past + i1 (masked to -inf downstream)
+void mul_mat_f16_exact(const __half *src0, int64_t ne00, int64_t ne01, int64_t ne02, int64_t nb01, int64_t nb02,
+                       const float *src1, int64_t ne11, int64_t ne12, int64_t nb11, int64_t nb12,
+                       float *dst, int64_t nbd1, int64_t nbd2, int causal_past, cudaStream_t st);
 
 }  // namespace b200

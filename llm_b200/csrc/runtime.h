@@ -22,6 +22,7 @@ struct Runtime {
     int device = 0, device_count = 0, sm_count = 0;
     cudaStream_t stream = nullptr;     // one non-blocking stream: every kernel and copy of this backend is ordered on it
     Arena op_arena;                    // per-node temporaries of the seam front end
+    bool fast = false;                 // B200_FAST=1: order-free integer-exact kernels (mmvq/mmq/attn.cu) instead of the bit-exact ones
     std::mutex mu;
     void ensure_init();                // exits(1) if there is no CUDA device: this backend has no CPU fallback
 };

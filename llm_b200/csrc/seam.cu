@@ -42,6 +42,7 @@ void Runtime::ensure_init() {
     cudaDeviceProp prop;
     B200_CHECK(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
+    { const char *f = getenv("B200_FAST"); fast = f && f[0] == '1'; }
     luts();
     inited = true;
 }
@@ -163,7 +164,8 @@ void op_mul_mat(const ggml_tensor *src0, const ggml_tensor *src1, ggml_tensor *d
         float2 *xds = (float2 *)R.op_arena.get((size_t)B * (K / QK) * sizeof(float2), st);
         const int64_t ldx = is_contiguous(src1) ? K : (int64_t)(src1->nb[1] / 4);
         quantize_act(vec_dot_type(src0->type), x, ldx, xq, xds, K, B, st);
-        if (B == 1)      mul_mat_vec_q(w, xq, xds, d, nullptr, st);
+        if (!R.fast)     mul_mat_q_exact(w, xq, xds, d, N, B, nullptr, 0, st);
+        else if (B == 1) mul_mat_vec_q(w, xq, xds, d, nullptr, st);
         else if (B < 16) mul_mat_q_simple(w, xq, xds, d, N, B, nullptr, 0, st);
         else             mul_mat_q(w, xq, xds, d, N, B, nullptr, 0, st);
         dst_finish(dst, d);
@@ -177,8 +179,10 @@ void op_mul_mat(const ggml_tensor *src0, const ggml_tensor *src1, ggml_tensor *d
         const float *b;
         if (on_device(src1)) b = (const float *)((Extra *)src1->extra)->data; else b = (const float *)src_dev(src1);
         float *d = (float *)dst_dev(dst);
-        mul_mat_f16(a, src0->ne[0], src0->ne[1], src0->ne[2], src0->nb[1], src0->nb[2],
-                    b, src1->ne[1], src1->ne[2], src1->nb[1], src1->nb[2], d, dst->nb[1], dst->nb[2], st);
+        if (R.fast) mul_mat_f16(a, src0->ne[0], src0->ne[1], src0->ne[2], src0->nb[1], src0->nb[2],
+                                b, src1->ne[1], src1->ne[2], src1->nb[1], src1->nb[2], d, dst->nb[1], dst->nb[2], st);
+        else mul_mat_f16_exact(a, src0->ne[0], src0->ne[1], src0->ne[2], src0->nb[1], src0->nb[2],
+                               b, src1->ne[1], src1->ne[2], src1->nb[1], src1->nb[2], d, dst->nb[1], dst->nb[2], -1, st);
         dst_finish(dst, d);
         return;
     }

@@ -70,6 +70,9 @@ struct b200_session {
     int32_t *h_tokens = nullptr; float *h_logits = nullptr;
     int last_launches = 0;
     int last_n = 0;
+    // debug taps (tests): copy one intermediate buffer of (layer, stage) aside during forward()
+    int tap_layer = -2, tap_stage = 0;
+    float *tap = nullptr; size_t tap_cap = 0, tap_count = 0;
 };
 
 bool b200_model::lookup(const char *name, Slot &s, int &slot_id) {
@@ -104,8 +107,9 @@ void silu_mul_rows(const float *h13, float *out, int64_t f, int64_t n, cudaStrea
 namespace {
 
 void mm(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda,
-        cudaStream_t st, Launches &L) {
-    if (B == 1)      mul_mat_vec_q(w, xq, xds, dst, addend, st);
+        cudaStream_t st, Launches &L, bool fast) {
+    if (!fast)       mul_mat_q_exact(w, xq, xds, dst, ldd, B, addend, lda, st);
+    else if (B == 1) mul_mat_vec_q(w, xq, xds, dst, addend, st);
     else if (B < 16) mul_mat_q_simple(w, xq, xds, dst, ldd, B, addend, lda, st);
     else             mul_mat_q(w, xq, xds, dst, ldd, B, addend, lda, st);
     L.n++;
@@ -122,17 +126,28 @@ void forward(b200_session *s, int n) {
     const float kq_scale = 1.0f / sqrtf((float)e / (float)n_head);                           // llama lib.rs:268-270
     const RopeTable &rope = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, hd, n_ctx);
     Launches L;
+    const bool fast = (s->cfg.flags & B200_SESSION_FAST) != 0;
+    int il = -1;
+    auto TAP = [&](int stage, const float *buf, size_t count) {
+        if (s->tap_layer != il || s->tap_stage != stage) return;
+        if (count > s->tap_cap) { if (s->tap) B200_CHECK(cudaFree(s->tap)); B200_CHECK(cudaMalloc(&s->tap, count * 4)); s->tap_cap = count; }
+        B200_CHECK(cudaMemcpyAsync(s->tap, buf, count * 4, cudaMemcpyDeviceToDevice, st));
+        s->tap_count = count;
+    };
 
     get_rows_q(m->wte, s->d_tokens, s->x, n, st); L.n++;                                      // :170
-    for (int il = 0; il < hp.n_layer; il++) {
+    for (il = 0; il < hp.n_layer; il++) {
         const Layer &ly = m->layers[il];
         __half *Kl = s->memory_k + (size_t)il * n_ctx * gqa;                                  // :227-231
         __half *Vl = s->memory_v + (size_t)il * n_ctx * gqa;                                  // :233-239
         rms_norm(s->x, s->cur, ly.attention_norm, e, n, 5e-6f, st); L.n++;                    // :183,186
+        TAP(1, s->cur, (size_t)n * e);
         quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-        mm(ly.wqkv, s->xq, s->xds, s->qkv, qkv_ld, n, nullptr, 0, st, L);                     // :194,208,223
+        mm(ly.wqkv, s->xq, s->xds, s->qkv, qkv_ld, n, nullptr, 0, st, L, fast);                     // :194,208,223
+        TAP(2, s->qkv, (size_t)n * qkv_ld);
         // RoPE on Q and K heads in place: [hd, n_head + n_head_kv, n] with row stride qkv_ld    :190-217
         rope_f32(s->qkv, s->qkv, hd, n_head + n_head_kv, n, hd, qkv_ld, hd, qkv_ld, n_past, rope, st); L.n++;
+        TAP(3, s->qkv, (size_t)n * qkv_ld);
         {   // store K (row per position) and V (transposed) into the f16 cache                   :243-244
             StridedDesc sk{{gqa, n, 1, 1}, {4, (int64_t)qkv_ld * 4, 0, 0}}, dk{{gqa, n, 1, 1}, {2, (int64_t)gqa * 2, 0, 0}};
             cpy_strided(s->qkv + e, T_F32, sk, Kl + (size_t)n_past * gqa, T_F16, dk, st); L.n++;
@@ -140,26 +155,43 @@ void forward(b200_session *s, int n) {
             cpy_strided(s->qkv + e + gqa, T_F32, sv, Vl + n_past, T_F16, dv, st); L.n++;
         }
         // KQ[h][i][j] = K[j][h] . f16(Q[i][h])                                                    :246-265
-        mul_mat_f16(Kl, hd, n_kv, n_head_kv, (int64_t)gqa * 2, (int64_t)hd * 2,
-                    s->qkv, n, n_head, (int64_t)qkv_ld * 4, (int64_t)hd * 4,
-                    s->kq, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4, st); L.n++;
+        if (fast) mul_mat_f16(Kl, hd, n_kv, n_head_kv, (int64_t)gqa * 2, (int64_t)hd * 2,
+                              s->qkv, n, n_head, (int64_t)qkv_ld * 4, (int64_t)hd * 4,
+                              s->kq, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4, st);
+        else mul_mat_f16_exact(Kl, hd, n_kv, n_head_kv, (int64_t)gqa * 2, (int64_t)hd * 2,
+                               s->qkv, n, n_head, (int64_t)qkv_ld * 4, (int64_t)hd * 4,
+                               s->kq, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4, n_past, st);
+        L.n++;
+        TAP(4, s->kq, (size_t)n_head * n * n_kv);
         soft_max(s->kq, s->kq, n_kv, (int64_t)n_head * n, n, kq_scale, true, n_past, true, true, st); L.n++;   // :268-281
+        TAP(5, s->kq, (size_t)n_head * n * n_kv);
         // KQV[h][i][c] = V[h][c][:] . f16(P[h][i][:]) written straight into the merged [n][e] layout     :284-307
-        mul_mat_f16(Vl, n_kv, hd, n_head_kv, (int64_t)n_ctx * 2, (int64_t)n_ctx * hd * 2,
-                    s->kq, n, n_head, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4,
-                    s->cur, (int64_t)e * 4, (int64_t)hd * 4, st); L.n++;
+        if (fast) mul_mat_f16(Vl, n_kv, hd, n_head_kv, (int64_t)n_ctx * 2, (int64_t)n_ctx * hd * 2,
+                              s->kq, n, n_head, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4,
+                              s->cur, (int64_t)e * 4, (int64_t)hd * 4, st);
+        else mul_mat_f16_exact(Vl, n_kv, hd, n_head_kv, (int64_t)n_ctx * 2, (int64_t)n_ctx * hd * 2,
+                               s->kq, n, n_head, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4,
+                               s->cur, (int64_t)e * 4, (int64_t)hd * 4, -1, st);
+        L.n++;
+        TAP(6, s->cur, (size_t)n * e);
         quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-        mm(ly.wo, s->xq, s->xds, s->ff, e, n, s->x, e, st, L);                                // :310,314  (inpFF = wo.cur + inpSA)
+        mm(ly.wo, s->xq, s->xds, s->ff, e, n, s->x, e, st, L, fast);                                // :310,314  (inpFF = wo.cur + inpSA)
+        TAP(7, s->ff, (size_t)n * e);
         rms_norm(s->ff, s->cur, ly.ffn_norm, e, n, 5e-6f, st); L.n++;                         // :318,321
+        TAP(8, s->cur, (size_t)n * e);
         quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-        mm(ly.w13, s->xq, s->xds, s->h13, 2 * f, n, nullptr, 0, st, L);                       // :323,325
+        mm(ly.w13, s->xq, s->xds, s->h13, 2 * f, n, nullptr, 0, st, L, fast);                       // :323,325
+        TAP(9, s->h13, (size_t)n * 2 * f);
         silu_mul_rows(s->h13, s->hmul, f, n, st); L.n++;                                      // :328,330  silu(w1 x) * (w3 x)
+        TAP(10, s->hmul, (size_t)n * f);
         quantize_act(vdt, s->hmul, f, s->xq, s->xds, f, n, st); L.n++;
-        mm(ly.w2, s->xq, s->xds, s->x, e, n, s->ff, e, st, L);                                // :332,334
+        mm(ly.w2, s->xq, s->xds, s->x, e, n, s->ff, e, st, L, fast);                                // :332,334
+        TAP(11, s->x, (size_t)n * e);
     }
+    il = -1;
     rms_norm(s->x, s->cur, m->norm, e, n, 5e-6f, st); L.n++;                                  // :343,346
     quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-    mm(m->output, s->xq, s->xds, s->logits, hp.n_vocab, n, nullptr, 0, st, L);                // :352
+    mm(m->output, s->xq, s->xds, s->logits, hp.n_vocab, n, nullptr, 0, st, L, fast);                // :352
     s->last_launches = L.n;
     s->last_n = n;
     s->n_past += n;                                                                           // inference_session.rs:288
@@ -440,12 +472,25 @@ int b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t 
     return B200_OK;
 }
 
+int b200_session_set_tap(b200_session *s, int32_t layer, int32_t stage) {
+    if (!s) return B200_ERR_BAD_ARG;
+    s->tap_layer = layer; s->tap_stage = stage; s->tap_count = 0;
+    return B200_OK;
+}
+int64_t b200_session_read_tap(b200_session *s, float *host_out, int64_t max_count) {
+    if (!s || !host_out) return B200_ERR_BAD_ARG;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    const size_t c = s->tap_count < (size_t)max_count ? s->tap_count : (size_t)max_count;
+    if (c) B200_CHECK(cudaMemcpy(host_out, s->tap, c * 4, cudaMemcpyDeviceToHost));
+    return (int64_t)c;
+}
+
 int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchronize(rt().stream)); return B200_OK; }
 
 void b200_session_free(b200_session *s) {
     if (!s) return;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
-    void *dev[] = {s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds};
+    void *dev[] = {s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
     if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));
@@ -488,8 +533,9 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
     float2 *xds = (float2 *)R.op_arena.get((size_t)B * (K / QK) * sizeof(float2), st);
     B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
     quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
-    if (impl == B200_MM_AUTO) impl = B == 1 ? B200_MM_VEC : (B < 16 ? B200_MM_SIMPLE : B200_MM_TENSOR);
-    if (impl == B200_MM_VEC) { for (int64_t b = 0; b < B; b++) mul_mat_vec_q(w, xq + b * K, xds + b * (K / QK), dd + b * N, nullptr, st); }
+    if (impl == B200_MM_AUTO) impl = B200_MM_EXACT;
+    if (impl == B200_MM_EXACT) mul_mat_q_exact(w, xq, xds, dd, N, B, nullptr, 0, st);
+    else if (impl == B200_MM_VEC) { for (int64_t b = 0; b < B; b++) mul_mat_vec_q(w, xq + b * K, xds + b * (K / QK), dd + b * N, nullptr, st); }
     else if (impl == B200_MM_SIMPLE) mul_mat_q_simple(w, xq, xds, dd, N, B, nullptr, 0, st);
     else mul_mat_q(w, xq, xds, dd, N, B, nullptr, 0, st);
     B200_CHECK(cudaMemcpyAsync(dst, dd, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));

@@ -171,8 +171,8 @@ class OrHparams(C.Structure):
 class Oracle:
     """The plain-C restatement (oracle/liboracle.so)."""
 
-    def __init__(self):
-        self.lib = L = C.CDLL(os.path.join(HERE, "liboracle.so"))
+    def __init__(self, libname="liboracle.so"):
+        self.lib = L = C.CDLL(os.path.join(HERE, libname))
         L.or_fp32_to_fp16.restype = C.c_uint16
         L.or_fp32_to_fp16.argtypes = [C.c_float]
         L.or_fp16_to_fp32.restype = C.c_float
@@ -204,6 +204,7 @@ class Oracle:
         L.or_llama_kv.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
         L.or_llama_free.argtypes = [C.c_void_p]
         L.or_llama_set_tap.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.or_llama_set_tap_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
 
     def fp32_to_fp16(self, x):
         return self.lib.or_fp32_to_fp16(float(x))
@@ -322,6 +323,17 @@ class OracleLlama:
             self.orc.lib.or_llama_set_tap(self.m, None, -2)
             return logits, tap
         return logits
+
+    def eval_tap(self, tokens, il, stage, count):
+        """eval and return (logits, flat f32 tap of `count` floats taken at (layer il, stage)); see llama_oracle.c"""
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        logits = np.empty((tokens.size, self.hp["n_vocab"]), np.float32)
+        tap = np.zeros(count, np.float32)
+        self.orc.lib.or_llama_set_tap_stage(self.m, _p(tap), il, stage)
+        rc = self.orc.lib.or_llama_eval(self.m, _p(tokens), tokens.size, _p(logits))
+        self.orc.lib.or_llama_set_tap_stage(self.m, None, -2, 11)
+        assert rc == 0
+        return logits, tap
 
     def kv(self, which):
         nb = C.c_size_t(0)

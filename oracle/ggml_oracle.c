@@ -222,6 +222,11 @@ void or_quantize_row_act(int t, const float *x, void *y, int64_t k) {
  * elements 4L..4L+3 (mul_sum_i8_pairs_float, LC/ggml.c:685-700: maddubs -> madd -> cvtepi32_ps, all exact),
  * accumulated with _mm256_fmadd_ps, reduced by hsum_float_8 (LC/ggml.c:608-616). ----------------------- */
 static inline float hsum8(const float a[8]) {
+#ifdef OR_PERTURB_HSUM
+    /* liboracle_perturbed.so only (tests/test_chaos.py): the SAME eight f32 values, added in a different association.  This is
+     * the smallest possible deviation from the reference (~1e-7 per mat-mul output) and is used to show what it does to logits. */
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+#endif
     const float r0 = a[4] + a[0], r1 = a[5] + a[1], r2 = a[6] + a[2], r3 = a[7] + a[3];
     const float s0 = r0 + r2, s1 = r1 + r3;
     return s0 + s1;

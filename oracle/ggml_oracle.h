@@ -76,5 +76,6 @@ void *or_llama_kv(or_llama *m, int which, size_t *nbytes);
 void  or_llama_free(or_llama *m);
 /* optional per-layer taps for debugging parity: copies the residual stream after layer il (or -1: final norm) */
 void  or_llama_set_tap(or_llama *m, float *buf, int il);
+void  or_llama_set_tap_stage(or_llama *m, float *buf, int il, int stage);
 
 #endif

@@ -22,14 +22,14 @@ struct or_llama {
     or_layer *layers;
     uint16_t *memory_k, *memory_v;
     int n_past;
-    float *tap; int tap_layer;
+    float *tap; int tap_layer, tap_stage;
 };
 
 static void *xmalloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "oracle: out of memory (%zu)\n", n); abort(); } return p; }
 
 or_llama *or_llama_new(const or_hparams *hp) {
     or_llama *m = calloc(1, sizeof(*m));
-    m->hp = *hp; m->tap_layer = -2;
+    m->hp = *hp; m->tap_layer = -2; m->tap_stage = 11;
     const int e = hp->n_embd, f = hp->n_ff, v = hp->n_vocab, t = hp->wtype;
     const int gqa = e / (hp->n_head / hp->n_head_kv);
     m->wte = xmalloc(or_row_bytes(t, e) * v);
@@ -74,7 +74,12 @@ void *or_llama_tensor(or_llama *m, const char *name, size_t *nbytes) {
 }
 
 void or_llama_reset(or_llama *m) { m->n_past = 0; }
-void or_llama_set_tap(or_llama *m, float *buf, int il) { m->tap = buf; m->tap_layer = il; }
+void or_llama_set_tap(or_llama *m, float *buf, int il) { m->tap = buf; m->tap_layer = il; m->tap_stage = 11; }
+/* stage taps inside layer il (debugging GPU parity): 1 cur after attn rms_norm*gain, 2 q|k|v before rope (q then k then v, each [N][.]),
+ * 3 q|k after rope, 4 KQ raw, 5 KQ after scale+mask+softmax, 6 merged KQV, 7 inpFF, 8 cur after ffn norm, 9 w1x|w3x, 10 silu*mul, 11 layer out */
+void or_llama_set_tap_stage(or_llama *m, float *buf, int il, int stage) { m->tap = buf; m->tap_layer = il; m->tap_stage = stage; }
+#define TAP(stage, ptr, count) do { if (m->tap && m->tap_layer == il && m->tap_stage == (stage)) memcpy(m->tap, (ptr), (size_t)(count) * 4); } while (0)
+#define TAP2(stage, p1, c1, p2, c2) do { if (m->tap && m->tap_layer == il && m->tap_stage == (stage)) { memcpy(m->tap, (p1), (size_t)(c1) * 4); memcpy(m->tap + (c1), (p2), (size_t)(c2) * 4); } } while (0)
 void *or_llama_kv(or_llama *m, int which, size_t *nbytes) {
     if (nbytes) *nbytes = (size_t)m->hp.n_embd * m->hp.n_layer * m->hp.n_ctx * 2;
     return which ? m->memory_v : m->memory_k;
@@ -106,11 +111,14 @@ int or_llama_eval(or_llama *m, const int32_t *tokens, int N, float *logits_all) 
         uint16_t *Vl = m->memory_v + (size_t)il * n_ctx * gqa;      /* [gqa][n_ctx] */
         or_rms_norm(x, cur, e, N, 5e-6f);                                                   /* :183 */
         mul_rows(cur, L->attention_norm, e, N);                                             /* :186 */
+        TAP(1, cur, (size_t)N * e);
         or_mul_mat(t, L->wq, cur, q, e, e, N);                                              /* :194 */
         or_mul_mat(t, L->wk, cur, k, e, gqa, N);                                            /* :208 */
         or_mul_mat(t, L->wv, cur, v, e, gqa, N);                                            /* :223 */
+        if (m->tap && m->tap_layer == il && m->tap_stage == 2) { memcpy(m->tap, q, (size_t)N*e*4); memcpy(m->tap + (size_t)N*e, k, (size_t)N*gqa*4); memcpy(m->tap + (size_t)N*(e+gqa), v, (size_t)N*gqa*4); }
         or_rope(q, hd, n_head, N, n_past, hp->n_rot, 0, 10000.0f, 1.0f);                    /* :190-203 */
         or_rope(k, hd, n_head_kv, N, n_past, hp->n_rot, 0, 10000.0f, 1.0f);                 /* :204-217 */
+        TAP2(3, q, (size_t)N * e, k, (size_t)N * gqa);
         for (int i = 0; i < N; i++)                                                         /* cpy f32->f16, :243-244 */
             for (int c = 0; c < gqa; c++) {
                 Kl[(size_t)(n_past + i) * gqa + c] = or_fp32_to_fp16(k[(size_t)i * gqa + c]);
@@ -126,7 +134,9 @@ int or_llama_eval(or_llama *m, const int32_t *tokens, int N, float *logits_all) 
                 for (int j = 0; j < n_kv; j++)
                     row[j] = or_vec_dot_f16(hd, Kl + (size_t)j * gqa + (size_t)hk * hd, q16 + (size_t)i * e + (size_t)h * hd);
             }
+        TAP(4, kq, (size_t)n_head * N * n_kv);
         or_scale_mask_soft_max(kq, n_kv, N, n_head, 1.0f / sqrtf((float)e / (float)n_head), n_past);  /* :268-281 */
+        TAP(5, kq, (size_t)n_head * N * n_kv);
         for (size_t i = 0; i < (size_t)n_head * N * n_kv; i++) p16[i] = or_fp32_to_fp16(kq[i]);
         #pragma omp parallel for collapse(2) schedule(static)
         for (int h = 0; h < n_head; h++)
@@ -139,17 +149,22 @@ int or_llama_eval(or_llama *m, const int32_t *tokens, int N, float *logits_all) 
         for (int i = 0; i < N; i++)                                                         /* permute + cpy, :299-307 */
             for (int h = 0; h < n_head; h++)
                 memcpy(cur + (size_t)i * e + (size_t)h * hd, kqv + ((size_t)h * N + i) * hd, (size_t)hd * 4);
+        TAP(6, cur, (size_t)N * e);
         or_mul_mat(t, L->wo, cur, ff, e, e, N);                                             /* :310 */
         for (size_t i = 0; i < (size_t)N * e; i++) ff[i] = ff[i] + x[i];                    /* inpFF, :314 */
+        TAP(7, ff, (size_t)N * e);
         or_rms_norm(ff, cur, e, N, 5e-6f);                                                  /* :318 */
         mul_rows(cur, L->ffn_norm, e, N);                                                   /* :321 */
+        TAP(8, cur, (size_t)N * e);
         or_mul_mat(t, L->w3, cur, h3, e, f, N);                                             /* :323 */
         or_mul_mat(t, L->w1, cur, h1, e, f, N);                                             /* :325 */
+        TAP2(9, h1, (size_t)N * f, h3, (size_t)N * f);
         or_silu(h1, h1, (int64_t)N * f);                                                    /* :328 */
         for (size_t i = 0; i < (size_t)N * f; i++) h1[i] = h1[i] * h3[i];                   /* :330 */
+        TAP(10, h1, (size_t)N * f);
         or_mul_mat(t, L->w2, h1, cur, f, e, N);                                             /* :332 */
         for (size_t i = 0; i < (size_t)N * e; i++) x[i] = cur[i] + ff[i];                   /* :334 */
-        if (m->tap && m->tap_layer == il) memcpy(m->tap, x, (size_t)N * e * 4);
+        TAP(11, x, (size_t)N * e);
     }
     or_rms_norm(x, cur, e, N, 5e-6f);                                                       /* :343 */
     mul_rows(cur, m->norm, e, N);                                                           /* :346 */

@@ -1,6 +1,8 @@
 """Whole-model parity on the GPU: the native session (include/llm_b200.h) and the reference executor running over our seam
 (oracle/_ref/libggml_seam.so) against the oracle, on the same seeded GGML weights.  Bar from BASELINE.json: logits within
-1e-3 relative of the reference ggml CPU path; we additionally require 1e-4 (f32 summation-order noise is ~1e-6)."""
+1e-3 relative of the reference ggml CPU path.  The reference graph amplifies any 1e-7 deviation to ~1e-2 (tests/test_chaos.py),
+so the default kernels reproduce the AVX2 operation order and the assertion here is BIT-EXACT logits and KV cache; the
+order-free fast mode is only required to stay at the reference's own chaos level."""
 import os
 
 import numpy as np
@@ -14,7 +16,8 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3        # north-star bar
-TIGHT = 1e-4      # what integer-exact kernels actually deliver, with margin
+CHAOS = 8e-2      # what ANY order-free implementation (incl. the reference's own NEON / CUDA paths) can be held to
+FAST = 4          # B200_SESSION_FAST
 
 
 def rel(g, c):
@@ -23,16 +26,22 @@ def rel(g, c):
 
 
 def check(g, c, what):
+    """default path: logits within 1e-3 -- and in fact identical bits"""
     mx, rms = rel(g, c)
     assert mx <= TOL and rms <= TOL, (what, mx, rms)
-    assert mx <= TIGHT, (what, "tight", mx, rms)
-    assert np.array_equal(g.argmax(-1), c.argmax(-1)), what
+    assert np.array_equal(g.view(np.uint32), c.view(np.uint32)), (what, "not bit-exact", mx, rms, int((g != c).sum()), g.size)
 
 
-def native(hp, tens, n_ctx, n_batch):
+def check_fast(g, c, what):
+    mx, rms = rel(g, c)
+    assert mx <= CHAOS and rms <= CHAOS, (what, mx, rms)
+    assert (g.argmax(-1) == c.argmax(-1)).mean() >= 0.9, what
+
+
+def native(hp, tens, n_ctx, n_batch, flags=0):
     import llm_b200
     m = llm_b200.Llama(hp, llm_b200.ModelParameters(context_size=n_ctx), tens)
-    return m, m.start_session(llm_b200.InferenceSessionConfig(n_batch=n_batch))
+    return m, m.start_session(llm_b200.InferenceSessionConfig(n_batch=n_batch, flags=flags))
 
 
 @pytest.mark.parametrize("name", ["q4_0", "q5_1"])
@@ -61,12 +70,23 @@ def test_native_vs_oracle(orc, cfg, name, n_prompt):
     for i in range(n_prompt, n_prompt + 4):                      # decode, each side on its OWN KV cache
         check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"decode{i}")
     check(s.evaluate(toks[n_prompt + 4:n_prompt + 6], all_logits=True), mo.eval(toks[n_prompt + 4:n_prompt + 6]), "pair")
-    # the f16 KV caches agree bit for bit except where an f32 value sat within summation noise of an fp16 rounding boundary
-    for which in (0, 1):
-        a, b = s.kv(which), mo.kv(which)
-        frac = float((a != b).mean())
-        assert frac < 2e-3, (which, frac)
+    for which in (0, 1):                                        # the f16 KV caches agree bit for bit
+        assert np.array_equal(s.kv(which), mo.kv(which)), which
     assert s.n_past == n_prompt + 6
+    s.close(); m.close()
+
+
+@pytest.mark.parametrize("cfg,name", [("tiny", "q4_0"), ("small", "q5_1")])
+def test_fast_mode_stays_at_chaos_level(orc, cfg, name):
+    """B200_SESSION_FAST: integer-exact block dots, free f32 summation order -> same error the reference shows against itself
+    when its own horizontal sum is re-associated (tests/test_chaos.py)"""
+    t = B.QUANT_TYPES[name]
+    hp, tens = synth.make_llama(synth.CONFIGS[cfg], t, orc.quantize)
+    toks = synth.make_tokens(hp, 50)
+    mo = orc.llama(hp, tens)
+    m, s = native(hp, tens, hp["n_ctx"], 64, FAST)
+    check_fast(s.evaluate(toks[:40], all_logits=True), mo.eval(toks[:40]), "fast prefill")
+    check_fast(s.evaluate(toks[40:41], all_logits=True), mo.eval(toks[40:41]), "fast decode")
     s.close(); m.close()
 
 
@@ -79,7 +99,7 @@ def test_session_semantics(orc):
     last = s.feed_prompt(toks[:100])
     mo = orc.llama(dict(hp, n_ctx=128), tens)
     want = mo.eval(toks[:100])[-1]
-    assert np.abs(last - want).max() / np.abs(want).max() <= TIGHT
+    assert np.array_equal(last, want)
     # ContextFull (inference_session.rs:311-313)
     with pytest.raises(llm_b200.ContextFull):
         s.feed_prompt(toks[100:140])

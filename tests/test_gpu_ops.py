@@ -1,8 +1,8 @@
 """Per-op parity of the CUDA kernels against the oracle, called THROUGH the C ABI:
   * the ggml_cuda_* seam with hand-built `struct ggml_tensor`s (llm_b200/ggml.py = the ctypes stub of the plugin API)
   * the b200_op_* host-buffer entry points.
-Bars: bit-exact for integer/byte results (activation quants, LUT ops); f32 results may differ from the CPU only by f32
-summation order -> rel error <= 2e-6 of the row scale (the oracle's own AVX lane order is no more canonical than ours)."""
+Bars: BIT-EXACT for the default kernels (exact.cu reproduces the AVX2 operation order) and for every integer/byte/LUT result;
+the order-free fast kernels (mmvq/mmq/attn.cu) are held to f32 summation noise (<= 2e-6 of the row scale)."""
 import ctypes as C
 
 import numpy as np
@@ -62,9 +62,24 @@ def test_quantize_act_bit_exact(L, orc, vdt):
 
 
 @pytest.mark.parametrize("name,t", TYPES)
+@pytest.mark.parametrize("K,N,Bn", [(4096, 200, 1), (11008, 96, 1), (256, 33, 5), (4096, 130, 37), (704, 100, 40), (64, 5, 3),
+                                     (4096, 257, 9), (5120, 64, 2)])
+def test_mul_mat_bit_exact(L, orc, name, t, K, N, Bn):
+    """default kernels: same bits as ggml_compute_forward_mul_mat on the reference's x86 build"""
+    rng = np.random.default_rng(K * 5 + N + t)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    x = (rng.standard_normal((Bn, K)) * rng.uniform(0.05, 8, (Bn, 1))).astype(np.float32)
+    wq = orc.quantize(t, w)
+    want = orc.mul_mat(t, wq, x)
+    got = np.empty((Bn, N), np.float32)
+    assert L.b200_op_mul_mat(t, wq.ctypes.data, K, N, x.ctypes.data, Bn, got.ctypes.data, 4) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, K, N, Bn, rel(got, want))
+
+
+@pytest.mark.parametrize("name,t", TYPES)
 @pytest.mark.parametrize("K,N,Bn,impl", [(4096, 200, 1, 1), (11008, 96, 1, 1), (256, 33, 5, 2), (4096, 130, 37, 3),
                                           (704, 100, 40, 3), (4096, 256, 128, 3), (4096, 64, 3, 1)])
-def test_mul_mat_vs_oracle(L, orc, name, t, K, N, Bn, impl):
+def test_mul_mat_fast_kernels_vs_oracle(L, orc, name, t, K, N, Bn, impl):
     rng = np.random.default_rng(K * 7 + N + t)
     w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     x = (rng.standard_normal((Bn, K)) * 2.5).astype(np.float32)
@@ -104,7 +119,7 @@ def test_seam_mul_mat_offloaded_weight(ctx, orc, name, t):
         dst = ctx.op_mul_mat(w, xt)
         assert ctx.compute(dst, nth=4) is True
         got = ctx.host_array(dst).reshape(Bn, N)
-        assert rel(got, orc.mul_mat(t, wq, x)) <= 2e-6
+        assert np.array_equal(got, orc.mul_mat(t, wq, x))
 
 
 def _gpu_src(ctx, a):
@@ -150,6 +165,27 @@ def test_seam_rope(ctx, golden_ops, tag):
     r = ctx.op_rope(_gpu_src(ctx, g[f"rope_{tag}_x"]), n_past, nd, mode); assert ctx.compute(r)
     got = ctx.host_array(r)
     assert np.array_equal(got.view(np.uint32), g[f"rope_{tag}"].view(np.uint32)), np.abs(got - g[f"rope_{tag}"]).max()
+
+
+def test_seam_mul_mat_f16_bit_exact(ctx, orc):
+    """the attention mat-muls: F16 src0 (KV cache views), f32 src1 rounded to fp16, ggml_vec_dot_f16 operation order"""
+    from llm_b200 import ggml
+    rng = np.random.default_rng(21)
+    for k, rows, n, heads in ((128, 70, 5, 4), (64, 33, 1, 3), (45, 64, 7, 2), (513, 128, 1, 2), (96, 16, 3, 1)):
+        a = rng.standard_normal((heads, rows, k)).astype(np.float16)
+        b = (rng.standard_normal((heads, n, k)) * 2).astype(np.float32)
+        at = ctx.transfer_to_gpu(ctx.new_tensor(ggml.F16, [k, rows, heads], a))
+        bt = ctx.from_numpy(b)
+        dst = ctx.op_mul_mat(at, bt)
+        assert ctx.compute(dst) is True
+        got = ctx.host_array(dst).reshape(heads, n, rows)
+        b16 = b.astype(np.float16)
+        want = np.empty_like(got)
+        for h in range(heads):
+            for i in range(n):
+                for r in range(rows):
+                    want[h, i, r] = orc.vec_dot_f16(a[h, r].view(np.uint16), b16[h, i].view(np.uint16))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (k, rows, n, heads, rel(got, want))
 
 
 def test_seam_rows_large(ctx, orc):
