@@ -37,6 +37,12 @@ void mul_mat_q_simple(const QWeight &w, const int8_t *xq, const float2 *xds, flo
 // same contract as mul_mat_q for any B >= 1; results are bit-identical to ggml_compute_forward_mul_mat on the reference's x86 build
 void mul_mat_q_exact(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 
+// ---- exact_stream.cu : the bit-exact decode mat-vec at HBM speed (TMA bulk-copy ring + AVX2 lane chains) ----------------------------
+bool mmv_exact_stream_supported(const QWeight &w);
+// bit-faithful activation quantizer emitting 16-byte records per (block, word): see exact_stream.cu
+void quantize_act_pack(int wtype, const float *x, int4 *pack, int64_t K, cudaStream_t st);
+void mul_mat_vec_q_exact_stream(const QWeight &w, const int4 *xpack, float *dst, const float *addend, cudaStream_t st);
+
 // ---- rowops.cu : warp/block-reduce kernels ------------------------------------------------------------------------
 struct Luts { const uint16_t *silu, *gelu, *exp; };   // 3 x 64 Ki fp16 tables built on the host with libm (LC/ggml.c:4313-4326)
 const Luts &luts();                                   // uploaded on first use

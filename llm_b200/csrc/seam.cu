@@ -160,6 +160,13 @@ void op_mul_mat(const ggml_tensor *src0, const ggml_tensor *src1, ggml_tensor *d
         }
         const float *x = (const float *)src_dev(src1);
         float *d = (float *)dst_dev(dst);
+        if (B == 1 && !R.fast && mmv_exact_stream_supported(w)) {      // decode: bit-exact streaming mat-vec
+            int4 *pack = (int4 *)R.op_arena.get((size_t)(K / QK) * 64, st);
+            quantize_act_pack(src0->type, x, pack, K, st);
+            mul_mat_vec_q_exact_stream(w, pack, d, nullptr, st);
+            dst_finish(dst, d);
+            return;
+        }
         int8_t *xq = (int8_t *)R.op_arena.get((size_t)B * K, st);
         float2 *xds = (float2 *)R.op_arena.get((size_t)B * (K / QK) * sizeof(float2), st);
         const int64_t ldx = is_contiguous(src1) ? K : (int64_t)(src1->nb[1] / 4);

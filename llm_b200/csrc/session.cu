@@ -65,9 +65,10 @@ struct b200_session {
     // activations (sized for n_batch rows)
     int32_t *d_tokens = nullptr;
     float *x = nullptr, *cur = nullptr, *ff = nullptr, *qkv = nullptr, *kq = nullptr, *h13 = nullptr, *hmul = nullptr, *logits = nullptr;
-    int8_t *xq = nullptr; float2 *xds = nullptr;
+    int8_t *xq = nullptr; float2 *xds = nullptr; int4 *xpack = nullptr;
     // pinned host staging
     int32_t *h_tokens = nullptr; float *h_logits = nullptr;
+    cudaEvent_t tokens_uploaded = nullptr;   // guards reuse of h_tokens by the next evaluate()
     int last_launches = 0;
     int last_n = 0;
     // debug taps (tests): copy one intermediate buffer of (layer, stage) aside during forward()
@@ -106,13 +107,21 @@ struct Launches { int n = 0; };
 void silu_mul_rows(const float *h13, float *out, int64_t f, int64_t n, cudaStream_t st);
 namespace {
 
-void mm(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda,
-        cudaStream_t st, Launches &L, bool fast) {
-    if (!fast)       mul_mat_q_exact(w, xq, xds, dst, ldd, B, addend, lda, st);
-    else if (B == 1) mul_mat_vec_q(w, xq, xds, dst, addend, st);
-    else if (B < 16) mul_mat_q_simple(w, xq, xds, dst, ldd, B, addend, lda, st);
-    else             mul_mat_q(w, xq, xds, dst, ldd, B, addend, lda, st);
-    L.n++;
+// ggml_mul_mat(w, x): quantize the f32 activation rows (the INIT phase of ggml_compute_forward_mul_mat) and multiply
+void matmul(b200_session *s, const QWeight &w, const float *x, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda,
+            cudaStream_t st, Launches &L, bool fast) {
+    if (B == 1 && !fast && mmv_exact_stream_supported(w)) {
+        quantize_act_pack(w.type, x, s->xpack, w.K, st);
+        mul_mat_vec_q_exact_stream(w, s->xpack, dst, addend, st);
+        L.n += 2;
+        return;
+    }
+    quantize_act(vec_dot_type(w.type), x, w.K, s->xq, s->xds, w.K, B, st);
+    if (!fast)       mul_mat_q_exact(w, s->xq, s->xds, dst, ldd, B, addend, lda, st);
+    else if (B == 1) mul_mat_vec_q(w, s->xq, s->xds, dst, addend, st);
+    else if (B < 16) mul_mat_q_simple(w, s->xq, s->xds, dst, ldd, B, addend, lda, st);
+    else             mul_mat_q(w, s->xq, s->xds, dst, ldd, B, addend, lda, st);
+    L.n += 2;
 }
 
 void forward(b200_session *s, int n) {
@@ -121,7 +130,6 @@ void forward(b200_session *s, int n) {
     cudaStream_t st = rt().stream;
     const int e = hp.n_embd, f = hp.n_ff, hd = m->hd, gqa = m->gqa, n_head = hp.n_head, n_head_kv = hp.n_head_kv;
     const int n_ctx = hp.context_size, n_past = s->n_past, n_kv = n_past + n;
-    const int vdt = vec_dot_type(hp.wtype);
     const int qkv_ld = e + 2 * gqa;
     const float kq_scale = 1.0f / sqrtf((float)e / (float)n_head);                           // llama lib.rs:268-270
     const RopeTable &rope = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, hd, n_ctx);
@@ -142,8 +150,7 @@ void forward(b200_session *s, int n) {
         __half *Vl = s->memory_v + (size_t)il * n_ctx * gqa;                                  // :233-239
         rms_norm(s->x, s->cur, ly.attention_norm, e, n, 5e-6f, st); L.n++;                    // :183,186
         TAP(1, s->cur, (size_t)n * e);
-        quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-        mm(ly.wqkv, s->xq, s->xds, s->qkv, qkv_ld, n, nullptr, 0, st, L, fast);                     // :194,208,223
+        matmul(s, ly.wqkv, s->cur, s->qkv, qkv_ld, n, nullptr, 0, st, L, fast);                // :194,208,223
         TAP(2, s->qkv, (size_t)n * qkv_ld);
         // RoPE on Q and K heads in place: [hd, n_head + n_head_kv, n] with row stride qkv_ld    :190-217
         rope_f32(s->qkv, s->qkv, hd, n_head + n_head_kv, n, hd, qkv_ld, hd, qkv_ld, n_past, rope, st); L.n++;
@@ -174,24 +181,20 @@ void forward(b200_session *s, int n) {
                                s->cur, (int64_t)e * 4, (int64_t)hd * 4, -1, st);
         L.n++;
         TAP(6, s->cur, (size_t)n * e);
-        quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-        mm(ly.wo, s->xq, s->xds, s->ff, e, n, s->x, e, st, L, fast);                                // :310,314  (inpFF = wo.cur + inpSA)
+        matmul(s, ly.wo, s->cur, s->ff, e, n, s->x, e, st, L, fast);                           // :310,314  (inpFF = wo.cur + inpSA)
         TAP(7, s->ff, (size_t)n * e);
         rms_norm(s->ff, s->cur, ly.ffn_norm, e, n, 5e-6f, st); L.n++;                         // :318,321
         TAP(8, s->cur, (size_t)n * e);
-        quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-        mm(ly.w13, s->xq, s->xds, s->h13, 2 * f, n, nullptr, 0, st, L, fast);                       // :323,325
+        matmul(s, ly.w13, s->cur, s->h13, 2 * f, n, nullptr, 0, st, L, fast);                  // :323,325
         TAP(9, s->h13, (size_t)n * 2 * f);
         silu_mul_rows(s->h13, s->hmul, f, n, st); L.n++;                                      // :328,330  silu(w1 x) * (w3 x)
         TAP(10, s->hmul, (size_t)n * f);
-        quantize_act(vdt, s->hmul, f, s->xq, s->xds, f, n, st); L.n++;
-        mm(ly.w2, s->xq, s->xds, s->x, e, n, s->ff, e, st, L, fast);                                // :332,334
+        matmul(s, ly.w2, s->hmul, s->x, e, n, s->ff, e, st, L, fast);                          // :332,334
         TAP(11, s->x, (size_t)n * e);
     }
     il = -1;
     rms_norm(s->x, s->cur, m->norm, e, n, 5e-6f, st); L.n++;                                  // :343,346
-    quantize_act(vdt, s->cur, e, s->xq, s->xds, e, n, st); L.n++;
-    mm(m->output, s->xq, s->xds, s->logits, hp.n_vocab, n, nullptr, 0, st, L, fast);                // :352
+    matmul(s, m->output, s->cur, s->logits, hp.n_vocab, n, nullptr, 0, st, L, fast);           // :352
     s->last_launches = L.n;
     s->last_n = n;
     s->n_past += n;                                                                           // inference_session.rs:288
@@ -257,20 +260,21 @@ float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches
     cudaStream_t st = rt().stream;
     const int e = m->hp.n_embd, f = m->hp.n_ff;
     // a valid quantized activation row for both K = n_embd and K = n_ff
+    const bool fast = (s->cfg.flags & B200_SESSION_FAST) != 0;
     B200_CHECK(cudaMemsetAsync(s->hmul, 0, (size_t)f * 4, st));
     quantize_act(vec_dot_type(m->hp.wtype), s->hmul, f, s->xq, s->xds, f, 1, st);
+    quantize_act_pack(m->hp.wtype, s->hmul, s->xpack, f, st);
     (void)e;
     int64_t n = 0;
+    auto mv = [&](const QWeight &w, float *out) {
+        if (fast) mul_mat_vec_q(w, s->xq, s->xds, out, nullptr, st);
+        else if (mmv_exact_stream_supported(w)) mul_mat_vec_q_exact_stream(w, s->xpack, out, nullptr, st);
+        else mul_mat_q_exact(w, s->xq, s->xds, out, w.N, 1, nullptr, 0, st);
+        n++;
+    };
     auto pass = [&]() {
-        for (auto &L : m->layers) {
-            mul_mat_vec_q(L.wqkv, s->xq, s->xds, s->qkv, nullptr, st);
-            mul_mat_vec_q(L.wo, s->xq, s->xds, s->ff, nullptr, st);
-            mul_mat_vec_q(L.w13, s->xq, s->xds, s->h13, nullptr, st);
-            mul_mat_vec_q(L.w2, s->xq, s->xds, s->cur, nullptr, st);
-            n += 4;
-        }
-        mul_mat_vec_q(m->output, s->xq, s->xds, s->logits, nullptr, st);
-        n += 1;
+        for (auto &L : m->layers) { mv(L.wqkv, s->qkv); mv(L.wo, s->ff); mv(L.w13, s->h13); mv(L.w2, s->cur); }
+        mv(m->output, s->logits);
     };
     pass();                      // warm-up (also first-touch of every page)
     n = 0;
@@ -408,8 +412,10 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMalloc(&s->logits, B * (size_t)hp.n_vocab * 4));
     B200_CHECK(cudaMalloc(&s->xq, B * kmax));
     B200_CHECK(cudaMalloc(&s->xds, B * (kmax / QK) * sizeof(float2)));
+    B200_CHECK(cudaMalloc(&s->xpack, (kmax / QK) * 64));
     B200_CHECK(cudaMallocHost(&s->h_tokens, B * 4));
     B200_CHECK(cudaMallocHost(&s->h_logits, B * (size_t)hp.n_vocab * 4));
+    B200_CHECK(cudaEventCreateWithFlags(&s->tokens_uploaded, cudaEventDisableTiming));
     rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
     return s;
 }
@@ -437,8 +443,10 @@ int b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, flo
     if (s->n_past + n > s->m->hp.context_size) return B200_ERR_CONTEXT_FULL;
     for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= s->m->hp.n_vocab) return B200_ERR_BAD_ARG;
     cudaStream_t st = rt().stream;
+    B200_CHECK(cudaEventSynchronize(s->tokens_uploaded));       // the previous (feed-only) call may still be reading the staging buffer
     memcpy(s->h_tokens, tokens, (size_t)n * 4);
     B200_CHECK(cudaMemcpyAsync(s->d_tokens, s->h_tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    B200_CHECK(cudaEventRecord(s->tokens_uploaded, st));
     forward(s, n);
     const size_t V = s->m->hp.n_vocab;
     if (logits_out) {
@@ -490,10 +498,11 @@ int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchroni
 void b200_session_free(b200_session *s) {
     if (!s) return;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
-    void *dev[] = {s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds};
+    void *dev[] = {s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
     if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));
+    if (s->tokens_uploaded) B200_CHECK(cudaEventDestroy(s->tokens_uploaded));
     delete s;
 }
 
@@ -534,7 +543,11 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
     B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
     quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
     if (impl == B200_MM_AUTO) impl = B200_MM_EXACT;
-    if (impl == B200_MM_EXACT) mul_mat_q_exact(w, xq, xds, dd, N, B, nullptr, 0, st);
+    if (impl == B200_MM_EXACT_STREAM) {
+        if (!mmv_exact_stream_supported(w)) return B200_ERR_BAD_ARG;
+        int4 *pack = (int4 *)R.op_arena.get((size_t)(K / QK) * 64, st);
+        for (int64_t b = 0; b < B; b++) { quantize_act_pack(wtype, dx + b * K, pack, K, st); mul_mat_vec_q_exact_stream(w, pack, dd + b * N, nullptr, st); }
+    } else if (impl == B200_MM_EXACT) mul_mat_q_exact(w, xq, xds, dd, N, B, nullptr, 0, st);
     else if (impl == B200_MM_VEC) { for (int64_t b = 0; b < B; b++) mul_mat_vec_q(w, xq + b * K, xds + b * (K / QK), dd + b * N, nullptr, st); }
     else if (impl == B200_MM_SIMPLE) mul_mat_q_simple(w, xq, xds, dd, N, B, nullptr, 0, st);
     else mul_mat_q(w, xq, xds, dd, N, B, nullptr, 0, st);

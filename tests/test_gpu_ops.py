@@ -77,6 +77,20 @@ def test_mul_mat_bit_exact(L, orc, name, t, K, N, Bn):
 
 
 @pytest.mark.parametrize("name,t", TYPES)
+@pytest.mark.parametrize("K,N,Bn", [(4096, 200, 1), (11008, 96, 2), (256, 33, 3), (5120, 1000, 1), (4096, 31, 1), (2048, 32, 1), (13824, 64, 1)])
+def test_mul_mat_stream_bit_exact(L, orc, name, t, K, N, Bn):
+    """decode mat-vec fed by TMA bulk copies (exact_stream.cu): same bits as the reference, any tile/chunk tail"""
+    rng = np.random.default_rng(K * 3 + N + t)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    x = (rng.standard_normal((Bn, K)) * rng.uniform(0.05, 8, (Bn, 1))).astype(np.float32)
+    wq = orc.quantize(t, w)
+    want = orc.mul_mat(t, wq, x)
+    got = np.empty((Bn, N), np.float32)
+    assert L.b200_op_mul_mat(t, wq.ctypes.data, K, N, x.ctypes.data, Bn, got.ctypes.data, 5) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, K, N, Bn, rel(got, want))
+
+
+@pytest.mark.parametrize("name,t", TYPES)
 @pytest.mark.parametrize("K,N,Bn,impl", [(4096, 200, 1, 1), (11008, 96, 1, 1), (256, 33, 5, 2), (4096, 130, 37, 3),
                                           (704, 100, 40, 3), (4096, 256, 128, 3), (4096, 64, 3, 1)])
 def test_mul_mat_fast_kernels_vs_oracle(L, orc, name, t, K, N, Bn, impl):
