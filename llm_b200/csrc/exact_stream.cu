@@ -1,223 +1,52 @@
 // llm_b200/csrc/exact_stream.cu -- the decode mat-vec at HBM speed WITH the reference's bit-exact operation order.
 //
-// Arithmetic = exact.cu (AVX2 lane chains of ggml_vec_dot_q*_q8_*).  Data movement is what changes:
-//   * a dedicated producer warp streams the weight rows of a 32-row tile chunk by chunk (32 quant blocks = 512 B of nibbles per
-//     row) into a 4-stage shared-memory ring with 16-byte cp.async (one warp instruction = one row's 512 contiguous bytes) and
-//     signals each stage through an mbarrier (cp.async.mbarrier.arrive): ~58 KB in flight per CTA without spending a register
-//     or an LSU slot of the compute warps on global loads.  (First version used one cp.async.bulk per row and per plane: 64
-//     TMA requests of 64..512 B per stage cost ~60 cycles each and capped the SM at ~9 GB/s -- profiles/r01_notes.md.)
+// Arithmetic = exact.cu (AVX2 lane chains of ggml_vec_dot_q*_q8_*).  Data movement is what changes (stream_core.cuh):
+//   * a dedicated producer warp streams the weight rows of a 32-row tile stage by stage (16 quant blocks = 256 B of nibbles per
+//     row) into a 4-stage shared-memory ring with 16-byte cp.async and signals each stage through an mbarrier
+//     (cp.async.mbarrier.arrive): the compute warps never touch global memory for weights.  The kernel is persistent: a CTA walks
+//     several row tiles and the ring keeps streaming across them.  (v1 used one cp.async.bulk per row and per plane: 64 TMA requests
+//     of 64..512 B per stage cost ~60 cycles each and capped the SM at ~9 GB/s -- profiles/r01_notes.md.)
 //   * 4 compute warps (4 threads per row: thread w owns AVX lanes w and w+4 == packed word w of every block) walk the blocks
-//     IN ORDER out of shared memory: 1 LDS.32 (nibbles) + 1 LDS.U16 (d) + 1 LDS.128 (activation pack) + 2 dp4a + 2 fma per block;
-//   * the quantized activation row is re-packed once per mat-vec (quantize_act_pack) into 16-byte records per (block, word):
-//     {x word w, x word w+4, -offset * (byte sums of both words) as 2 x int16 | s, d_x}, so the -8 / -16 nibble offsets ride in
-//     the dp4a accumulator and need no per-block unpack arithmetic.
-// Algorithmic bytes per row of K weights: K/32 * {18, 20, 22, 24, 34}; each is read exactly once.
-#include "kernels.cuh"
+//     IN ORDER out of shared memory: 3 LDS + 3 unpack + 2 dp4a + 2 i2f + 1 cvt + 1 fmul + 2 fma per block;
+//   * the quantized activation row is re-packed once per mat-vec (quantize_act_pack) into 16-byte records per (block, word).
+// Algorithmic bytes per row of K weights: K/32 * {18, 20, 22, 24, 34}; each is read exactly once (ncu: dram bytes == algorithmic).
+#include "stream_core.cuh"
 
 namespace b200 {
 
+using namespace stream;
+
 namespace {
 
-constexpr int SR = 32;        // rows per tile
-constexpr int SCB = 16;       // quant blocks per ring stage
-constexpr int SST = 4;        // ring stages
-constexpr int SCOMPUTE = 128; // 4 compute warps (4 threads per row)
-constexpr int STHREADS = SCOMPUTE + 32;
-
-template <int TYPE> struct St {
-    static constexpr int QS = (TYPE == T_Q8_0) ? 32 : 16;
-    static constexpr int DM = (TYPE == T_Q4_1 || TYPE == T_Q5_1) ? 4 : 2;
-    static constexpr bool QH = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
-    static constexpr bool MIN = (TYPE == T_Q4_1 || TYPE == T_Q5_1);
-    static constexpr int QS_STRIDE = SCB * QS + 16;     // +16 B: the 8 rows of a warp land in different banks
-    static constexpr int DM_STRIDE = SCB * DM + 16;
-    static constexpr int QH_STRIDE = SCB * 4 + 16;
-    static constexpr int QS_BYTES = SR * QS_STRIDE, DM_BYTES = SR * DM_STRIDE, QH_BYTES = QH ? SR * QH_STRIDE : 0;
-    static constexpr int STAGE_BYTES = QS_BYTES + DM_BYTES + QH_BYTES;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void cp16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-// arrive on `bar` once all cp.async issued so far by this thread have landed (counts against the barrier's expected arrivals)
-__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-
-// One plane of a stage: SR rows x (COLS x 16 B), global row pitch src_pitch bytes, shared row pitch dst_pitch.  No divisions:
-// COLS is a power of two, a warp instruction covers 32/COLS rows (COLS <= 32) or half a row (COLS == 64).
-template <int COLS>
-__device__ __forceinline__ void stream_plane(uint32_t dst, int dst_pitch, const uint8_t *src, int64_t src_pitch, int cols_valid, int rows_valid, int lane) {
-    if (COLS >= 32) {
-#pragma unroll 8
-        for (int rr = 0; rr < SR; rr++) {
-            const uint8_t *srow = src + (int64_t)(rr < rows_valid ? rr : rows_valid - 1) * src_pitch;      // tail tile: re-read a valid row
-#pragma unroll
-            for (int k = 0; k < COLS / 32; k++) { const int cc = lane + 32 * k; if (cc < cols_valid) cp16(dst + rr * dst_pitch + cc * 16, srow + cc * 16); }
-        }
-    } else {
-        constexpr int RPI = 32 / COLS;
-        const int r0 = lane / COLS, cc = lane % COLS;
-#pragma unroll
-        for (int it = 0; it < SR / RPI; it++) {
-            const int rr = it * RPI + r0;
-            const uint8_t *srow = src + (int64_t)(rr < rows_valid ? rr : rows_valid - 1) * src_pitch;
-            if (cc < cols_valid) cp16(dst + rr * dst_pitch + cc * 16, srow + cc * 16);
-        }
-    }
-}
-
-// Persistent kernel: CTA `blockIdx.x` owns the row tiles blockIdx.x, +gridDim.x, ...; the ring keeps streaming across tiles.
 template <int TYPE>
 __global__ void __launch_bounds__(STHREADS) mmv_exact_stream_kernel(const QWeight w, const int4 *__restrict__ xpack, float *__restrict__ dst,
                                                                     const float *__restrict__ addend) {
     using T = St<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *full = (uint64_t *)smem, *empty = full + SST;
-    uint8_t *ring = smem + 128;
-    const int nb = (int)w.nb;
-    int4 *sx = (int4 *)(ring + SST * T::STAGE_BYTES);     // [nb][4] activation records
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nchunks = (nb + SCB - 1) / SCB;
-    const int ntiles = (int)((w.N + SR - 1) / SR);
-
-    if (tid == 0) {
-        for (int s = 0; s < SST; s++) { mbar_init(&full[s], 32); mbar_init(&empty[s], SCOMPUTE / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST, smem + 128, 0u};
+    int4 *sx = (int4 *)(R.base + T::RING_BYTES);          // [nb][4] activation records
+    const int tid = threadIdx.x;
+    if (tid == 0) ring_init(R.full, R.empty);
     __syncthreads();
-
-    if (warp == SCOMPUTE / 32) {
-        // ===== producer warp: 16-byte cp.async straight from HBM/L2 into the ring; completion through the stage's mbarrier =====
-        uint32_t g = 0;                                                     // running stage counter across tiles
-        const uint32_t ring_u32 = smem_u32(ring);
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t row_base = (int64_t)tile * SR;
-            const int rows_valid = (int)(w.N - row_base < SR ? w.N - row_base : SR);
-            for (int c = 0; c < nchunks; c++, g++) {
-                const int s = g % SST;
-                const int b0 = c * SCB, cb = nb - b0 < SCB ? nb - b0 : SCB;
-                mbar_wait(&empty[s], ((g / SST) & 1) ^ 1);
-                const uint32_t st = ring_u32 + s * T::STAGE_BYTES;
-                stream_plane<SCB * T::QS / 16>(st, T::QS_STRIDE, w.qs + (row_base * nb + b0) * T::QS, (int64_t)nb * T::QS, cb * T::QS / 16, rows_valid, lane);
-                stream_plane<SCB * T::DM / 16>(st + T::QS_BYTES, T::DM_STRIDE, (const uint8_t *)w.dm + (row_base * nb + b0) * T::DM, (int64_t)nb * T::DM,
-                                               cb * T::DM / 16, rows_valid, lane);
-                if (T::QH)
-                    stream_plane<SCB * 4 / 16>(st + T::QS_BYTES + T::DM_BYTES, T::QH_STRIDE, (const uint8_t *)(w.qh + row_base * nb + b0), (int64_t)nb * 4,
-                                               cb * 4 / 16, rows_valid, lane);
-                cp_async_arrive(&full[s]);
-            }
-        }
-        return;
-    }
-
-    // ===== compute warps =====
-    for (int i = tid; i < nb * 4; i += SCOMPUTE) sx[i] = __ldg(xpack + i);           // activation records -> shared memory (once per CTA)
-    asm volatile("bar.sync 1, %0;" ::"n"(SCOMPUTE));                                 // compute warps only
-    const int r = tid >> 2, wd = tid & 3;
-    uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        float a_lo = 0.f, a_hi = 0.f, summs = 0.f;
-        for (int c = 0; c < nchunks; c++, g++) {
-            const int s = g % SST;
-            const int b0 = c * SCB, cb = nb - b0 < SCB ? nb - b0 : SCB;
-            mbar_wait(&full[s], (g / SST) & 1);
-            const uint8_t *st = ring + s * T::STAGE_BYTES;
-            const uint8_t *qrow = st + r * T::QS_STRIDE, *drow = st + T::QS_BYTES + r * T::DM_STRIDE, *hrow = st + T::QS_BYTES + T::DM_BYTES + r * T::QH_STRIDE;
-#pragma unroll 8
-            for (int b = 0; b < cb; b++) {
-                const int4 xp = sx[(b0 + b) * 4 + wd];
-                float dw, mw = 0.f;
-                if (T::MIN) { const __half2 dm = *(const __half2 *)(drow + b * 4); dw = __low2float(dm); mw = __high2float(dm); }
-                else dw = __half2float(*(const __half *)(drow + b * 2));
-                int s_lo, s_hi;
-                if (TYPE == T_Q8_0) {
-                    s_lo = __dp4a(*(const int *)(qrow + b * 32 + 4 * wd), xp.x, 0);
-                    s_hi = __dp4a(*(const int *)(qrow + b * 32 + 16 + 4 * wd), xp.y, 0);
-                } else if (TYPE == T_Q4_0) {
-                    // (q - 8) as a 4-bit two's complement value is q ^ 8; parked in the HIGH nibble of each byte it reads as 16*(q-8):
-                    // the dp4a result is exactly 16 * sum (q-8) x, and the 1/16 rides (exactly, a power of two) in the packed d_x.
-                    const uint32_t q = *(const uint32_t *)(qrow + b * 16 + 4 * wd);
-                    s_lo = __dp4a((int)(((q << 4) ^ 0x80808080u) & 0xF0F0F0F0u), xp.x, 0);
-                    s_hi = __dp4a((int)((q ^ 0x88888888u) & 0xF0F0F0F0u), xp.y, 0);
-                } else {
-                    const uint32_t q = *(const uint32_t *)(qrow + b * 16 + 4 * wd);
-                    uint32_t l = q & 0x0F0F0F0Fu, h = (q >> 4) & 0x0F0F0F0Fu;
-                    if (T::QH) {
-                        const uint32_t qh = *(const uint32_t *)(hrow + b * 4);
-                        l |= spread4_to_bit4(qh >> (4 * wd));
-                        h |= spread4_to_bit4(qh >> (16 + 4 * wd));
-                    }
-                    // Q5_0: the -16 offset of every value is pre-multiplied into the accumulator seeds (exact integers); Q4_1/Q5_1: no offset
-                    const int seed_lo = TYPE == T_Q5_0 ? (int)(short)(xp.z & 0xffff) : 0;
-                    const int seed_hi = TYPE == T_Q5_0 ? (xp.z >> 16) : 0;
-                    s_lo = __dp4a((int)l, xp.x, seed_lo);
-                    s_hi = __dp4a((int)h, xp.y, seed_hi);
-                }
-                const float d = __fmul_rn(dw, __int_as_float(xp.w));
-                a_lo = __fmaf_rn(d, (float)s_lo, a_lo);
-                a_hi = __fmaf_rn(d, (float)s_hi, a_hi);
-                if (T::MIN) summs = __fmaf_rn(mw, __int_as_float(xp.z), summs);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-        float v = __fadd_rn(a_hi, a_lo);                                   // hsum_float_8 (see exact.cu)
-        v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
-        v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
-        if (T::MIN) v = __fadd_rn(v, summs);
-        const int64_t row = (int64_t)tile * SR + r;
-        if (wd == 0 && row < w.N) dst[row] = addend ? __fadd_rn(v, addend[row]) : v;
-    }
+    if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31); return; }
+    for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) sx[i] = __ldg(xpack + i);
+    compute_sync();
+    consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
+        if ((tid & 3) == 0 && row < w.N) dst[row] = addend ? __fadd_rn(v, addend[row]) : v;
+    });
 }
 
-// ---- activation quantizer that emits the packed records (one warp per block; arithmetic identical to quantize_act) ----------------
-// record (block b, word w) = { x bytes 4w..4w+3, x bytes 16+4w..16+4w+3, z, d_x }:
-//   z = 2 x int16 { -off * sum(bytes of word w), -off * sum(bytes of word w+4) }   for Q8_0 activations (off = 8: Q4_0, 16: Q5_0, 0: Q8_0)
-//   z = bits of s = d * sum(q)                                                      for Q8_1 activations (Q4_1 / Q5_1)
 __global__ void __launch_bounds__(256) quantize_act_pack_kernel(const float *__restrict__ x, int4 *__restrict__ pack, int nbk, int q81, int off, int scale16) {
     const int blk = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blk >= nbk) return;
     const int lane = threadIdx.x & 31;
-    const float v = x[blk * QK + lane];
-    const float amax = warp_max(fabsf(v));
-    const float d = __fdiv_rn(amax, 127.f);
-    const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
-    const int q = __float2int_rn(__fmul_rn(v, id));
-    const int isum = warp_sum(q);
-    uint32_t word = (uint32_t)(q & 0xff) << (8 * (lane & 3));
-    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-    word |= __shfl_xor_sync(0xffffffffu, word, 2);
-    int s4 = q + __shfl_xor_sync(0xffffffffu, q, 1);
-    s4 += __shfl_xor_sync(0xffffffffu, s4, 2);
-    const uint32_t word_hi = __shfl_down_sync(0xffffffffu, word, 16);
-    const int s4_hi = __shfl_down_sync(0xffffffffu, s4, 16);
-    if (lane < 16 && (lane & 3) == 0) {
-        const int wd = lane >> 2;
-        int4 rec;
-        rec.x = (int)word; rec.y = (int)word_hi;
-        if (q81) { rec.z = __float_as_int(__fmul_rn(d, (float)isum)); rec.w = __float_as_int(d); }
-        else {
-            rec.z = (int)(((uint32_t)(-off * s4) & 0xffffu) | ((uint32_t)(-off * s4_hi) << 16));
-            const float dx = __half2float(__float2half_rn(d));
-            rec.w = __float_as_int(scale16 ? dx * 0.0625f : dx);       // Q4_0 consumer computes 16 * dot: fold the exact 1/16 here
-        }
-        pack[blk * 4 + wd] = rec;
-    }
+    pack_block(x[blk * QK + lane], pack + blk * 4, lane, q81, off, scale16);
 }
 
 template <int TYPE>
 void launch_stream(const QWeight &w, const int4 *xpack, float *dst, const float *addend, cudaStream_t st) {
     using T = St<TYPE>;
-    const int smem = 128 + SST * T::STAGE_BYTES + (int)w.nb * 64;
+    const int smem = 128 + T::RING_BYTES + (int)w.nb * 64;
     static int smem_set = 0;
     if (smem > smem_set) {
         B200_ASSERT(smem <= 227 * 1024);
@@ -237,12 +66,11 @@ void launch_stream(const QWeight &w, const int4 *xpack, float *dst, const float 
 
 }  // namespace
 
-bool mmv_exact_stream_supported(const QWeight &w) { return w.nb % 8 == 0 && w.nb * 64 + 128 + SST * St<T_Q8_0>::STAGE_BYTES <= 227 * 1024; }
+bool mmv_exact_stream_supported(const QWeight &w) { return w.nb % 8 == 0 && w.nb * 64 + 128 + St<T_Q8_0>::RING_BYTES <= 227 * 1024; }
 
 void quantize_act_pack(int wtype, const float *x, int4 *pack, int64_t K, cudaStream_t st) {
     const int nbk = (int)(K / QK);
-    const int off = wtype == T_Q5_0 ? 16 : 0;
-    quantize_act_pack_kernel<<<(nbk + 7) / 8, 256, 0, st>>>(x, pack, nbk, has_min(wtype) ? 1 : 0, off, wtype == T_Q4_0 ? 1 : 0);
+    quantize_act_pack_kernel<<<(nbk + 7) / 8, 256, 0, st>>>(x, pack, nbk, has_min(wtype) ? 1 : 0, wtype == T_Q5_0 ? 16 : 0, wtype == T_Q4_0 ? 1 : 0);
     B200_CHECK(cudaGetLastError());
 }
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/llm_b200.h"
+#include "decode.h"
 #include "kernels.cuh"
 #include "runtime.h"
 
@@ -72,6 +73,12 @@ struct b200_session {
     int last_launches = 0;
     int last_n = 0;
     // debug taps (tests): copy one intermediate buffer of (layer, stage) aside during forward()
+    // one-launch-per-token decode kernel (decode.cu)
+    DecodeLayer *d_layers = nullptr; unsigned int *d_bar = nullptr; int *d_n_past = nullptr; int *h_n_past = nullptr;
+    float *qbuf = nullptr, *attn = nullptr;
+    int dev_n_past = -1;             // value currently held by *d_n_past (-1: unknown)
+    bool mega_ok = false; int mega_grid = 0;
+    DecodeParams dp;
     int tap_layer = -2, tap_stage = 0;
     float *tap = nullptr; size_t tap_cap = 0, tap_count = 0;
 };
@@ -135,6 +142,19 @@ void forward(b200_session *s, int n) {
     const RopeTable &rope = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, hd, n_ctx);
     Launches L;
     const bool fast = (s->cfg.flags & B200_SESSION_FAST) != 0;
+    if (n == 1 && s->mega_ok && !fast && !(s->cfg.flags & B200_SESSION_UNFUSED) && s->tap_layer == -2) {
+        // decode: the whole token in one persistent cooperative kernel (decode.cu)
+        if (s->dev_n_past != n_past) {
+            *s->h_n_past = n_past;
+            B200_CHECK(cudaMemcpyAsync(s->d_n_past, s->h_n_past, sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        if (launch_decode(s->dp, hp.wtype, st, &s->mega_grid)) {
+            s->dev_n_past = n_past + 1;
+            s->last_launches = 1; s->last_n = 1; s->n_past += 1;
+            return;
+        }
+        s->mega_ok = false;
+    }
     int il = -1;
     auto TAP = [&](int stage, const float *buf, size_t count) {
         if (s->tap_layer != il || s->tap_stage != stage) return;
@@ -416,7 +436,34 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMallocHost(&s->h_tokens, B * 4));
     B200_CHECK(cudaMallocHost(&s->h_logits, B * (size_t)hp.n_vocab * 4));
     B200_CHECK(cudaEventCreateWithFlags(&s->tokens_uploaded, cudaEventDisableTiming));
-    rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
+    const RopeTable &rt_ = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
+    // decode kernel parameters
+    B200_CHECK(cudaMalloc(&s->qbuf, e * 4));
+    B200_CHECK(cudaMalloc(&s->attn, e * 4));
+    B200_CHECK(cudaMalloc(&s->d_bar, 2 * sizeof(unsigned int)));
+    B200_CHECK(cudaMemset(s->d_bar, 0, 2 * sizeof(unsigned int)));
+    B200_CHECK(cudaMalloc(&s->d_n_past, sizeof(int)));
+    B200_CHECK(cudaMallocHost(&s->h_n_past, sizeof(int)));
+    {
+        std::vector<DecodeLayer> hl(hp.n_layer);
+        for (int il = 0; il < hp.n_layer; il++) {
+            const Layer &L = m->layers[il];
+            hl[il] = DecodeLayer{L.wqkv, L.wo, L.w13, L.w2, L.attention_norm, L.ffn_norm,
+                                 s->memory_k + (size_t)il * n_ctx * gqa, s->memory_v + (size_t)il * n_ctx * gqa};
+        }
+        B200_CHECK(cudaMalloc(&s->d_layers, hl.size() * sizeof(DecodeLayer)));
+        B200_CHECK(cudaMemcpy(s->d_layers, hl.data(), hl.size() * sizeof(DecodeLayer), cudaMemcpyHostToDevice));
+    }
+    DecodeParams &P = s->dp;
+    P.layers = s->d_layers; P.n_layer = hp.n_layer; P.wte = m->wte; P.output = m->output; P.norm = m->norm;
+    P.e = (int)e; P.f = (int)f; P.hd = m->hd; P.gqa = m->gqa; P.n_head = hp.n_head; P.n_head_kv = hp.n_head_kv; P.n_ctx = (int)n_ctx; P.n_vocab = hp.n_vocab;
+    P.kq_scale = 1.0f / sqrtf((float)hp.n_embd / (float)hp.n_head); P.eps = 5e-6f;
+    P.rope_cs = rt_.cs; P.rope_half = rt_.half;
+    P.lut_silu = luts().silu; P.lut_exp = luts().exp;
+    P.token = s->d_tokens; P.n_past = s->d_n_past;
+    P.x = s->x; P.q = s->qbuf; P.kq = s->kq; P.attn = s->attn; P.ff = s->ff; P.h13 = s->h13; P.logits = s->logits;
+    P.bar = s->d_bar;
+    s->mega_ok = hp.n_rot == m->hd && decode_supported(P, hp.wtype);
     return s;
 }
 
@@ -498,7 +545,8 @@ int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchroni
 void b200_session_free(b200_session *s) {
     if (!s) return;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
-    void *dev[] = {s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack};
+    if (s->h_n_past) B200_CHECK(cudaFreeHost(s->h_n_past));
+    void *dev[] = {s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
     if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));

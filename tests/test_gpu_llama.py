@@ -76,6 +76,36 @@ def test_native_vs_oracle(orc, cfg, name, n_prompt):
     s.close(); m.close()
 
 
+@pytest.mark.parametrize("cfg,name", [("tiny8", "q4_0"), ("tiny8", "q4_1"), ("tiny8", "q5_0"), ("tiny8", "q5_1"), ("tiny8", "q8_0"), ("gqa8", "q4_0"), ("gqa8", "q5_1")])
+def test_decode_kernel_bit_exact(orc, cfg, name):
+    """the one-launch-per-token persistent kernel (decode.cu): prefill then 40 decode steps, each side on its own KV cache"""
+    t = B.QUANT_TYPES[name]
+    hp, tens = synth.make_llama(synth.CONFIGS[cfg], t, orc.quantize)
+    toks = synth.make_tokens(hp, 70)
+    mo = orc.llama(hp, tens)
+    m, s = native(hp, tens, hp["n_ctx"], 64)
+    check(s.evaluate(toks[:21], all_logits=True), mo.eval(toks[:21]), "prefill")
+    for i in range(21, 61):
+        g = s.evaluate(toks[i:i + 1], all_logits=True)
+        assert s.last_launches == 1, "decode kernel not used"
+        check(g, mo.eval(toks[i:i + 1]), f"decode{i}")
+    for which in (0, 1):
+        assert np.array_equal(s.kv(which), mo.kv(which)), which
+    # rewind + re-decode, then a batch, then decode again (device-side n_past must follow)
+    s.rewind(30); mo.reset(); mo.eval(toks[:30])
+    check(s.evaluate(toks[30:31], all_logits=True), mo.eval(toks[30:31]), "after rewind")
+    check(s.evaluate(toks[31:35], all_logits=True), mo.eval(toks[31:35]), "batch4")
+    check(s.evaluate(toks[35:36], all_logits=True), mo.eval(toks[35:36]), "decode after batch")
+    # the per-op schedule gives the same bits
+    m2, s2 = native(hp, tens, hp["n_ctx"], 64, flags=2)
+    s2.evaluate(toks[:35])
+    a = s2.evaluate(toks[35:36], all_logits=True)
+    assert s2.last_launches > 1
+    mo.reset(); mo.eval(toks[:35])
+    check(a, mo.eval(toks[35:36]), "unfused")
+    s.close(); m.close(); s2.close(); m2.close()
+
+
 @pytest.mark.parametrize("cfg,name", [("tiny", "q4_0"), ("small", "q5_1")])
 def test_fast_mode_stays_at_chaos_level(orc, cfg, name):
     """B200_SESSION_FAST: integer-exact block dots, free f32 summation order -> same error the reference shows against itself
@@ -169,5 +199,7 @@ def test_7b_geometry_two_layers(orc):
     mo = orc.llama(hp, tens)
     m, s = native(hp, tens, hp["n_ctx"], 64)
     check(s.evaluate(toks[:64], all_logits=True), mo.eval(toks[:64]), "7b-2l prefill")
-    check(s.evaluate(toks[64:65], all_logits=True), mo.eval(toks[64:65]), "7b-2l decode")
+    for i in range(64, 68):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"7b-2l decode {i}")
+        assert s.last_launches == 1
     s.close(); m.close()
