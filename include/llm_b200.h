@@ -42,8 +42,9 @@ typedef struct {
 } b200_session_config;
 
 enum {
-    B200_SESSION_NO_GRAPH = 1,     /* do not capture decode steps as CUDA graphs (debug) */
-    B200_SESSION_UNFUSED  = 2,     /* one kernel per reference graph node (the seam's kernels) instead of the fused schedule */
+    B200_SESSION_NO_GRAPH = 1,     /* launch the decode kernels one by one instead of replaying the captured CUDA graph (debug) */
+    B200_SESSION_UNFUSED  = 2,     /* decode with the prefill schedule (one kernel per reference graph node, the seam's kernels) */
+    B200_SESSION_MEGA     = 8,     /* experimental: one persistent cooperative kernel per decoded token (decode.cu) instead of the graph */
     B200_SESSION_FAST     = 4,     /* order-free kernels: integer-exact block dots but a different f32 summation order than the
                                       reference's AVX2 build.  NOT conformant: the reference graph amplifies 1e-7 differences to ~1e-2
                                       in the logits (DESIGN.md "chaos").  Default (flag clear) = bit-exact kernels. */
@@ -88,6 +89,9 @@ int  b200_session_set_n_past(b200_session *s, int32_t n_past);   /* rewind (supp
 /* raw f16 KV cache bytes (get_snapshot, inference_session.rs:599-646): which = 0 memory_k, 1 memory_v */
 int  b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t nbytes);
 int  b200_session_sync(b200_session *s);
+/* with B200_DECODE_PROF=1 in the environment the decode kernel stamps %globaltimer (ns) at its phase boundaries (CTA 0);
+ * slot 0 = start, then pairs (before / after grid barrier) per phase in graph order, slot 127 = end of token */
+int  b200_session_decode_profile(b200_session *s, unsigned long long *out128);
 /* debug taps for parity work: keep a copy of one intermediate buffer of (layer, stage) during the next evaluate.
  * stages: 1 attn-norm out [n][e], 2 qkv before rope [n][e+2gqa], 3 qkv after rope, 4 KQ raw [h][n][n_kv], 5 KQ softmax, 6 merged
  * KQV [n][e], 7 inpFF, 8 ffn-norm out, 9 [w1x | w3x] [n][2f], 10 silu*mul [n][f], 11 layer output [n][e] */

@@ -46,26 +46,6 @@ __device__ __forceinline__ void grid_sync(unsigned int *bar, int tid) {
     compute_sync();
 }
 
-__device__ __forceinline__ float cta_rms_scale(const float *x, int n, float eps, double *shd, int tid) {
-    double s = 0.0;
-    for (int i = tid; i < n; i += SCOMPUTE) { const float v = __ldcg(x + i); s += (double)__fmul_rn(v, v); }
-    s = warp_sum(s);
-    if ((tid & 31) == 0) shd[tid >> 5] = s;
-    compute_sync();
-    const double tot = (shd[0] + shd[1]) + (shd[2] + shd[3]);
-    compute_sync();
-    const float mean = (float)(tot / (double)n);
-    return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-}
-
-template <int TYPE, class F>
-__device__ __forceinline__ void build_pack(int4 *sx, int nbk, F val, int tid) {
-    const int lane = tid & 31;
-    for (int b = tid >> 5; b < nbk; b += SCOMPUTE / 32)
-        pack_block(val(b * QK + lane), sx + b * 4, lane, has_min(TYPE) ? 1 : 0, TYPE == T_Q5_0 ? 16 : 0, TYPE == T_Q4_0 ? 1 : 0);
-    compute_sync();
-}
-
 // element i (i < 16: low half, element i and i+16 of the block) of one quant block of a planes matrix (dequantize_row_*, LC/ggml.c:1525-1635)
 template <int TYPE>
 __device__ __forceinline__ void dequant_pair(const QWeight &w, int64_t blk, int j, float &lo, float &hi) {
@@ -95,13 +75,14 @@ template <int TYPE>
 __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodeParams P) {
     using T = St<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST, smem + 128, 0u};
-    double *shd = (double *)(smem + 64);                       // 8 doubles of reduction scratch
-    uint8_t *scratch = R.base + T::RING_BYTES;                 // activation records (mat-vec phases) | attention scratch (phases B, C)
+    constexpr int DST = (TYPE == T_Q8_0) ? 5 : 8;              // ring depth: ~80 KB of weights in flight per CTA (2 CTAs / SM)
+    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST_MAX, smem + 256, 0u, DST};
+    double *shd = (double *)(smem + 128);                      // 8 doubles of reduction scratch (behind the 16 mbarriers)
+    uint8_t *scratch = R.base + T::ring_bytes(DST);                 // activation records (mat-vec phases) | attention scratch (phases B, C)
     int4 *sx = (int4 *)scratch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, ncta = gridDim.x;
-    if (tid == 0) ring_init(R.full, R.empty);
+    if (tid == 0) ring_init(R.full, R.empty, DST);
     __syncthreads();
 
     if (tid >= SCOMPUTE) {
@@ -110,7 +91,7 @@ __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodePara
             const DecodeLayer *L = P.layers + il;
             { const QWeight w = L->wqkv; produce_matvec<TYPE>(w, R, cta, ncta, lane); }
             { const QWeight w = L->wo;   produce_matvec<TYPE>(w, R, cta, ncta, lane); }
-            { const QWeight w = L->w13;  produce_matvec<TYPE>(w, R, cta, ncta, lane); }
+            { const QWeight w = L->w13;  produce_matvec<TYPE>(w, R, cta, ncta, lane, 2); }
             { const QWeight w = L->w2;   produce_matvec<TYPE>(w, R, cta, ncta, lane); }
         }
         produce_matvec<TYPE>(P.output, R, cta, ncta, lane);
@@ -121,6 +102,61 @@ __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodePara
     const int e = P.e, f = P.f, hd = P.hd, gqa = P.gqa, n_ctx = P.n_ctx;
     const int p = __ldcg(P.n_past), n_kv = p + 1;
     const int tok = __ldcg(P.token);
+    int pslot = 0;
+    auto mark = [&]() {
+        if (P.prof && cta == 0 && tid == 0 && pslot < 127) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.prof[pslot] = t; }
+        pslot++;
+    };
+    mark();
+    float *sv = (float *)(scratch + (size_t)(e / QK) * 64);     // [e] staged activation vector, right behind the e-sized record array
+    float *stash = (float *)(scratch + (size_t)P.scratch_bytes - 256); // 64 floats at the very end of the scratch area
+
+    // rms_norm(src) * gain -> quantize -> records in sx.  The vector and the gain are fetched with ALL loads in flight (registers),
+    // the normalised row goes through shared memory, then each warp quantizes every 4th block (ggml_rms_norm + ggml_mul + the
+    // INIT-phase quantize_row_q8_* of the following mul_mat; LC/ggml.c:10129-10175, 1217-1300).
+    constexpr int MAXV = 12;                                    // float4 per thread: n_embd <= 6144
+    auto norm_pack = [&](const float *src, const float *gain) {
+        float4 xv[MAXV], gv[MAXV];
+        const int nv4 = e / 4;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            const int i = tid + k * SCOMPUTE;
+            if (i < nv4) { xv[k] = __ldcg((const float4 *)src + i); gv[k] = __ldg((const float4 *)gain + i); }
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXV; k++)
+            if (tid + k * SCOMPUTE < nv4) {
+                s += (double)__fmul_rn(xv[k].x, xv[k].x); s += (double)__fmul_rn(xv[k].y, xv[k].y);
+                s += (double)__fmul_rn(xv[k].z, xv[k].z); s += (double)__fmul_rn(xv[k].w, xv[k].w);
+            }
+        s = warp_sum(s);
+        if (lane == 0) shd[warp] = s;
+        compute_sync();
+        const double tot = (shd[0] + shd[1]) + (shd[2] + shd[3]);
+        const float mean = (float)(tot / (double)e);
+        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+#pragma unroll
+        for (int k = 0; k < MAXV; k++) {
+            const int i = tid + k * SCOMPUTE;
+            if (i < nv4) {
+                float4 y;
+                y.x = __fmul_rn(__fmul_rn(xv[k].x, scale), gv[k].x); y.y = __fmul_rn(__fmul_rn(xv[k].y, scale), gv[k].y);
+                y.z = __fmul_rn(__fmul_rn(xv[k].z, scale), gv[k].z); y.w = __fmul_rn(__fmul_rn(xv[k].w, scale), gv[k].w);
+                ((float4 *)sv)[i] = y;
+            }
+        }
+        compute_sync();
+        for (int b0 = warp * 4; b0 < e / QK; b0 += SCOMPUTE / 8) {           // 4 blocks per warp pass (e / 32 is a multiple of 4)
+            const int b = b0 + (lane >> 3);
+            pack_quad(((const float4 *)sv)[b * 8 + (lane & 7)], sx + b * 4, lane, true, has_min(TYPE) ? 1 : 0, TYPE == T_Q5_0 ? 16 : 0, TYPE == T_Q4_0 ? 1 : 0);
+        }
+        compute_sync();
+    };
+    auto load_pack = [&](const int4 *src, int nbk) {           // records produced by an earlier phase (global, L2) -> sx
+        for (int i = tid; i < nbk * 4; i += SCOMPUTE) sx[i] = __ldcg(src + i);
+        compute_sync();
+    };
 
     // embedding row: get_rows(tok_embeddings, token)                                             llama lib.rs:170
     for (int b = cta; b < e / QK; b += ncta)
@@ -130,15 +166,15 @@ __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodePara
             P.x[b * QK + tid] = lo; P.x[b * QK + tid + 16] = hi;
         }
     grid_sync(P.bar, tid);
+    mark();
 
     for (int il = 0; il < P.n_layer; il++) {
         const DecodeLayer *L = P.layers + il;
         __half *Kl = L->K, *Vl = L->V;
         // ---- A: attention norm -> QKV mat-vec -> RoPE + KV store ----
         {
-            const float scale = cta_rms_scale(P.x, e, P.eps, shd, tid);
-            const float *gain = L->attn_norm;
-            build_pack<TYPE>(sx, e / QK, [&](int i) { return __fmul_rn(__fmul_rn(__ldcg(P.x + i), scale), __ldg(gain + i)); }, tid);
+            norm_pack(P.x, L->attn_norm);
+            mark();
             const QWeight w = L->wqkv;
             consume_matvec<TYPE>(w, sx, R, cta, ncta, tid, [&](int64_t row, float v) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, 4);          // the rotation partner: rows 2i and 2i+1 sit in adjacent quads
@@ -156,42 +192,49 @@ __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodePara
                 }
             });
         }
-        grid_sync(P.bar, tid);
-        // ---- B: KQ[h][j] = K[j][h] . f16(Q[h])  (ggml_vec_dot_f16 order), 64 cached positions per work item ----
+        mark(); grid_sync(P.bar, tid); mark();
+        // ---- B: KQ[h][j] = K[j][h] . f16(Q[h])  (ggml_vec_dot_f16 order); work item = 64 cached positions of one head ----
         {
             __half *q16 = (__half *)scratch;
+            __half *kt = (__half *)(scratch + 512);                 // [64][hd] staged K rows
             const int chunks = (n_kv + 63) / 64, items = P.n_head * chunks;
+            const int vec_per_row = hd / 8;                         // 16-byte vectors per K row
             for (int it = cta; it < items; it += ncta) {
                 const int h = it / chunks, j0 = (it - h * chunks) * 64;
                 const int hk = h / (P.n_head / P.n_head_kv);
+                const int rows = n_kv - j0 < 64 ? n_kv - j0 : 64;
                 for (int i = tid; i < hd; i += SCOMPUTE) q16[i] = __float2half_rn(__ldcg(P.q + h * hd + i));
+                for (int i = tid; i < rows * vec_per_row; i += SCOMPUTE) {       // all 16-byte loads of the tile in flight at once
+                    const int rr = i / vec_per_row, cc = i - rr * vec_per_row;
+                    ((int4 *)kt)[rr * vec_per_row + cc] = __ldcg((const int4 *)(Kl + (int64_t)(j0 + rr) * gqa + hk * hd) + cc);
+                }
                 compute_sync();
                 const int np = hd & ~31;
-                for (int jj = 0; jj < 16; jj++) {
-                    const int j = j0 + warp * 16 + jj;
-                    if (j >= n_kv) break;
-                    const __half *krow = Kl + (int64_t)j * gqa + hk * hd;
+                for (int jj = warp; jj < rows; jj += SCOMPUTE / 32) {
+                    const __half *krow = kt + jj * hd;
                     float s = 0.f;
-                    for (int k = lane; k < np; k += 32) s = __fmaf_rn(__half2float(__ldcg(krow + k)), __half2float(q16[k]), s);
+                    for (int k = lane; k < np; k += 32) s = __fmaf_rn(__half2float(krow[k]), __half2float(q16[k]), s);
                     s = f16dot_tree(s);
                     if (lane == 0) {
                         double sumf = (double)s;
-                        for (int k = np; k < hd; k++) sumf += (double)__fmul_rn(__half2float(__ldcg(krow + k)), __half2float(q16[k]));
-                        P.kq[(int64_t)h * n_ctx + j] = (float)sumf;
+                        for (int k = np; k < hd; k++) sumf += (double)__fmul_rn(__half2float(krow[k]), __half2float(q16[k]));
+                        P.kq[(int64_t)h * n_ctx + j0 + jj] = (float)sumf;
                     }
                 }
                 compute_sync();
             }
         }
-        grid_sync(P.bar, tid);
-        // ---- C: scale, soft_max, KQV for 32 channels of one head per work item ----
+        mark(); grid_sync(P.bar, tid); mark();
+        // ---- C: scale, soft_max, KQV for 32 channels of one head per work item; the 32 outputs are one quant block of wo's input ----
         {
-            float *sc = (float *)scratch;                       // [n_kv] exp values
+            constexpr int KC = 128;                              // cached positions per staged V tile
+            float *sc = (float *)scratch;                        // [n_kv] exp values
             __half *p16 = (__half *)(scratch + (size_t)n_ctx * 4);
+            __half *vt = (__half *)(scratch + (size_t)n_ctx * 6);   // [32][KC]
             float *shf = (float *)shd;
-            const int cpi = 32, per_head = hd / cpi, items = P.n_head * per_head;
+            const int per_head = hd / 32, items = P.n_head * per_head;
             for (int it = cta; it < items; it += ncta) {
-                const int h = it / per_head, c0 = (it - h * per_head) * cpi;
+                const int h = it / per_head, c0 = (it - h * per_head) * 32;
                 const int hk = h / (P.n_head / P.n_head_kv);
                 float mx = -INFINITY;
                 for (int j = tid; j < n_kv; j += SCOMPUTE) { const float v = __fmul_rn(__ldcg(P.kq + (int64_t)h * n_ctx + j), P.kq_scale); sc[j] = v; mx = fmaxf(mx, v); }
@@ -199,7 +242,6 @@ __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodePara
                 if (lane == 0) shf[warp] = mx;
                 compute_sync();
                 mx = fmaxf(fmaxf(shf[0], shf[1]), fmaxf(shf[2], shf[3]));
-                compute_sync();
                 double s = 0.0;
                 for (int j = tid; j < n_kv; j += SCOMPUTE) { const float ev = lutf(P.lut_exp, __fsub_rn(sc[j], mx)); sc[j] = ev; s += (double)ev; }
                 s = warp_sum(s);
@@ -207,70 +249,114 @@ __global__ void __launch_bounds__(STHREADS) llama_decode_kernel(const DecodePara
                 compute_sync();
                 const float inv = (float)(1.0 / ((shd[4] + shd[5]) + (shd[6] + shd[7])));
                 for (int j = tid; j < n_kv; j += SCOMPUTE) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
-                compute_sync();
                 const int np = n_kv & ~31;
-                for (int cc = 0; cc < cpi / 4; cc++) {
-                    const int c = c0 + warp * (cpi / 4) + cc;
-                    const __half *vrow = Vl + (int64_t)(hk * hd + c) * n_ctx;
-                    float a = 0.f;
-                    for (int k = lane; k < np; k += 32) a = __fmaf_rn(__half2float(__ldcg(vrow + k)), __half2float(p16[k]), a);
-                    a = f16dot_tree(a);
-                    if (lane == 0) {
-                        double sumf = (double)a;
-                        for (int k = np; k < n_kv; k++) sumf += (double)__fmul_rn(__half2float(__ldcg(vrow + k)), __half2float(p16[k]));
-                        P.attn[h * hd + c] = (float)sumf;
+                float acc[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) acc[cc] = 0.f;
+                // leftover columns [np, n_kv) of the 32 V rows, fetched up front (one 16-byte vector per thread)
+                __half *vleft = vt + 32 * KC;                     // [32][32]
+                if (np < n_kv) {
+                    const int rr = tid >> 2, part = tid & 3;
+                    ((int4 *)vleft)[tid] = __ldcg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + np) + part);
+                }
+                int4 pre[KC / 32];                                 // next V tile, prefetched into registers while the current one is consumed
+                auto fetch = [&](int k0) {
+#pragma unroll
+                    for (int u = 0; u < KC / 32; u++) {
+                        const int i = tid + u * SCOMPUTE, rr = i / (KC / 8), cc = i - rr * (KC / 8);
+                        pre[u] = __ldcg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + k0) + cc);
+                    }
+                };
+                if (np > 0) fetch(0);
+                for (int k0 = 0; k0 < np; k0 += KC) {
+                    compute_sync();                                // p16 complete / previous tile consumed
+#pragma unroll
+                    for (int u = 0; u < KC / 32; u++) ((int4 *)vt)[tid + u * SCOMPUTE] = pre[u];
+                    compute_sync();
+                    if (k0 + KC < np) fetch(k0 + KC);
+                    const int kend = np - k0 < KC ? np - k0 : KC;
+#pragma unroll
+                    for (int cc = 0; cc < 8; cc++) {
+                        const __half *vrow = vt + (warp * 8 + cc) * KC;
+                        for (int k = lane; k < kend; k += 32) acc[cc] = __fmaf_rn(__half2float(vrow[k]), __half2float(p16[k0 + k]), acc[cc]);
                     }
                 }
                 compute_sync();
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) {
+                    const float a = f16dot_tree(acc[cc]);
+                    if (lane == 0) {
+                        const __half *vrow = vleft + (warp * 8 + cc) * 32;
+                        double sumf = (double)a;
+                        for (int k = np; k < n_kv; k++) sumf += (double)__fmul_rn(__half2float(vrow[k - np]), __half2float(p16[k]));
+                        stash[warp * 8 + cc] = (float)sumf;
+                    }
+                }
+                compute_sync();
+                if (warp == 0)
+                    pack_quad(((const float4 *)stash)[lane & 7], P.xpack_d + (int64_t)((h * hd + c0) / QK) * 4, lane, lane < 8, has_min(TYPE) ? 1 : 0,
+                              TYPE == T_Q5_0 ? 16 : 0, TYPE == T_Q4_0 ? 1 : 0);
+                compute_sync();
             }
         }
-        grid_sync(P.bar, tid);
+        mark(); grid_sync(P.bar, tid); mark();
         // ---- D: wo + residual ----
         {
-            build_pack<TYPE>(sx, e / QK, [&](int i) { return __ldcg(P.attn + i); }, tid);
+            load_pack(P.xpack_d, e / QK);
+            mark();
             const QWeight w = L->wo;
             consume_matvec<TYPE>(w, sx, R, cta, ncta, tid, [&](int64_t row, float v) {
                 if ((tid & 3) == 0 && row < w.N) P.ff[row] = __fadd_rn(v, __ldcg(P.x + row));
             });
         }
-        grid_sync(P.bar, tid);
-        // ---- E: ffn norm -> [w1|w3] ----
+        mark(); grid_sync(P.bar, tid); mark();
+        // ---- E: ffn norm -> [w1|w3] (rows interleaved in 32-row chunks: a pair of tiles = w1 x and w3 x for the same 32 channels)
+        //         -> silu(w1 x) * (w3 x) quantized right here: one block of w2's input per tile pair ----
         {
-            const float scale = cta_rms_scale(P.ff, e, P.eps, shd, tid);
-            const float *gain = L->ffn_norm;
-            build_pack<TYPE>(sx, e / QK, [&](int i) { return __fmul_rn(__fmul_rn(__ldcg(P.ff + i), scale), __ldg(gain + i)); }, tid);
+            norm_pack(P.ff, L->ffn_norm);
+            mark();
             const QWeight w = L->w13;
             consume_matvec<TYPE>(w, sx, R, cta, ncta, tid, [&](int64_t row, float v) {
-                if ((tid & 3) == 0 && row < w.N) P.h13[row] = v;
-            });
+                if ((tid & 3) == 0) stash[row & 63] = v;
+                if (((row >> 5) & 1) == 0) return;                                 // first tile of the pair: keep going
+                compute_sync();
+                if (warp == 0) {
+                    const int w8 = lane & 7;
+                    const float4 a = ((const float4 *)stash)[w8], b = ((const float4 *)stash)[8 + w8];
+                    float4 hm;                                                     // silu(w1 x) * (w3 x)  (:328-330)
+                    hm.x = __fmul_rn(lutf(P.lut_silu, a.x), b.x); hm.y = __fmul_rn(lutf(P.lut_silu, a.y), b.y);
+                    hm.z = __fmul_rn(lutf(P.lut_silu, a.z), b.z); hm.w = __fmul_rn(lutf(P.lut_silu, a.w), b.w);
+                    pack_quad(hm, P.xpack_f + (row >> 6) * 4, lane, lane < 8, has_min(TYPE) ? 1 : 0, TYPE == T_Q5_0 ? 16 : 0, TYPE == T_Q4_0 ? 1 : 0);
+                }
+                compute_sync();
+            }, 2);
         }
-        grid_sync(P.bar, tid);
-        // ---- F: silu(w1 x) * (w3 x) -> w2 + residual ----
+        mark(); grid_sync(P.bar, tid); mark();
+        // ---- F: w2 + residual ----
         {
-            build_pack<TYPE>(sx, f / QK, [&](int i) { return __fmul_rn(lutf(P.lut_silu, __ldcg(P.h13 + i)), __ldcg(P.h13 + f + i)); }, tid);
+            load_pack(P.xpack_f, f / QK);
+            mark();
             const QWeight w = L->w2;
             consume_matvec<TYPE>(w, sx, R, cta, ncta, tid, [&](int64_t row, float v) {
                 if ((tid & 3) == 0 && row < w.N) P.x[row] = __fadd_rn(v, __ldcg(P.ff + row));
             });
         }
-        grid_sync(P.bar, tid);
+        mark(); grid_sync(P.bar, tid); mark();
     }
     // ---- final norm -> lm_head ----
     {
-        const float scale = cta_rms_scale(P.x, e, P.eps, shd, tid);
-        build_pack<TYPE>(sx, e / QK, [&](int i) { return __fmul_rn(__fmul_rn(__ldcg(P.x + i), scale), __ldg(P.norm + i)); }, tid);
+        norm_pack(P.x, P.norm);
         consume_matvec<TYPE>(P.output, sx, R, cta, ncta, tid, [&](int64_t row, float v) {
             if ((tid & 3) == 0 && row < P.output.N) P.logits[row] = v;
         });
     }
+    if (P.prof && cta == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.prof[127] = t; }
     if (cta == 0 && tid == 0) *P.n_past = p + 1;               // InferenceSession::n_past += 1 (inference_session.rs:288)
 }
 
 template <int TYPE>
 int decode_smem_bytes(const DecodeParams &P) {
-    const size_t sxb = (size_t)((P.f > P.e ? P.f : P.e) / QK) * 64;
-    const size_t att = (size_t)P.n_ctx * 6 + 512;
-    return (int)(128 + St<TYPE>::RING_BYTES + (sxb > att ? sxb : att));
+    return (int)(256 + St<TYPE>::ring_bytes(TYPE == T_Q8_0 ? 5 : 8) + P.scratch_bytes);
 }
 
 template <int TYPE>
@@ -296,7 +382,17 @@ bool launch_decode_t(const DecodeParams &P, cudaStream_t st, int *grid_out) {
 
 }  // namespace
 
+int decode_scratch_bytes(int e, int f, int hd, int n_ctx) {
+    size_t a = (size_t)(e / QK) * 64 + (size_t)e * 4;        // records + staged vector (phases A, E, final)
+    size_t b = (size_t)(f / QK) * 64;                          // records of w2's input (phase F)
+    size_t c = 512 + (size_t)64 * hd * 2;                      // q16 + staged K tile (phase B)
+    size_t d = (size_t)n_ctx * 6 + 32 * 128 * 2 + 32 * 32 * 2;  // exp values, fp16 probabilities, staged V tile + leftover columns (phase C)
+    size_t m = a; if (b > m) m = b; if (c > m) m = c; if (d > m) m = d;
+    return (int)(((m + 255) & ~(size_t)255) + 256);            // + 64 floats of epilogue stash at the end
+}
+
 bool decode_supported(const DecodeParams &P, int wtype) {
+    if (P.e > 6144 || P.e % 128 || P.f % 32 || P.hd % 32 || P.n_ctx % 128 || P.hd > 256) return false;
     QWeight probe; probe.nb = P.e / QK;
     QWeight probe2; probe2.nb = P.f / QK;
     return is_quant(wtype) && mmv_exact_stream_supported(probe) && mmv_exact_stream_supported(probe2) && P.hd % 2 == 0 && P.hd <= 256 && P.e % 64 == 0 &&

@@ -1,5 +1,7 @@
 // llm_b200/csrc/decode.h -- parameters of the one-launch-per-token decode kernel (decode.cu)
 #pragma once
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace b200 {
@@ -22,11 +24,18 @@ struct DecodeParams {
     const int32_t *token;
     int *n_past;                        // device copy of InferenceSession::n_past; incremented at the end of the kernel
     float *x, *q, *kq, *attn, *ff, *h13, *logits;
+    int scratch_bytes;                  // decode_scratch_bytes(): per-CTA shared memory behind the weight ring
+    int4 *xpack_d, *xpack_f;            // activation records produced by phase C (for wo) and phase E (for w2)
     unsigned int *bar;                  // [0] arrival count, [1] generation
+    unsigned long long *prof;           // optional: %globaltimer stamps of CTA 0 at phase boundaries (debug / tuning), 128 slots
 };
 
+int decode_scratch_bytes(int e, int f, int hd, int n_ctx);
 bool decode_supported(const DecodeParams &P, int wtype);
 // cooperative launch on `st`; returns false if the kernel cannot be made resident (caller falls back to the per-op schedule)
 bool launch_decode(const DecodeParams &P, int wtype, cudaStream_t st, int *grid_out);
+
+// default decode schedule: 8 fused kernels per layer on `st` (decode_ops.cu); position read from *P.n_past on the device
+void decode_ops_enqueue(const DecodeParams &P, const std::vector<DecodeLayer> &layers, int wtype, int n_kv_bucket, int4 *xpack_a, cudaStream_t st, int *launches);
 
 }  // namespace b200

@@ -23,10 +23,10 @@ __global__ void __launch_bounds__(STHREADS) mmv_exact_stream_kernel(const QWeigh
                                                                     const float *__restrict__ addend) {
     using T = St<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST, smem + 128, 0u};
+    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST_MAX, smem + 256, 0u, SST};
     int4 *sx = (int4 *)(R.base + T::RING_BYTES);          // [nb][4] activation records
     const int tid = threadIdx.x;
-    if (tid == 0) ring_init(R.full, R.empty);
+    if (tid == 0) ring_init(R.full, R.empty, SST);
     __syncthreads();
     if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31); return; }
     for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) sx[i] = __ldg(xpack + i);
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) quantize_act_pack_kernel(const float *__r
 template <int TYPE>
 void launch_stream(const QWeight &w, const int4 *xpack, float *dst, const float *addend, cudaStream_t st) {
     using T = St<TYPE>;
-    const int smem = 128 + T::RING_BYTES + (int)w.nb * 64;
+    const int smem = 256 + T::RING_BYTES + (int)w.nb * 64;
     static int smem_set = 0;
     if (smem > smem_set) {
         B200_ASSERT(smem <= 227 * 1024);
@@ -66,7 +66,7 @@ void launch_stream(const QWeight &w, const int4 *xpack, float *dst, const float 
 
 }  // namespace
 
-bool mmv_exact_stream_supported(const QWeight &w) { return w.nb % 8 == 0 && w.nb * 64 + 128 + St<T_Q8_0>::RING_BYTES <= 227 * 1024; }
+bool mmv_exact_stream_supported(const QWeight &w) { return w.nb % 8 == 0 && w.nb * 64 + 256 + St<T_Q8_0>::RING_BYTES <= 227 * 1024; }
 
 void quantize_act_pack(int wtype, const float *x, int4 *pack, int64_t K, cudaStream_t st) {
     const int nbk = (int)(K / QK);

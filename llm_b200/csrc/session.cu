@@ -53,7 +53,9 @@ struct b200_model {
     std::vector<uint8_t> loaded;        // per tensor slot
     int n_loaded = 0;
 
-    struct Slot { QWeight q; float *f = nullptr; int64_t n = 0; bool is_q = false; };
+    // chunk > 0: the tensor's rows live in `chunk`-row pieces, piece c at rows [c * stride + q_row0, + chunk) of the matrix `q`
+    // (w1 / w3 are interleaved in 32-row pieces inside w13 so that 64 consecutive rows hold both factors of 32 silu*mul outputs)
+    struct Slot { QWeight q; float *f = nullptr; int64_t n = 0; bool is_q = false; int chunk = 0; int64_t row0 = 0, stride = 0, rows = 0; };
     bool lookup(const char *name, Slot &s, int &slot_id);
     int n_slots() const { return 3 + 9 * hp.n_layer; }
 };
@@ -74,10 +76,16 @@ struct b200_session {
     int last_n = 0;
     // debug taps (tests): copy one intermediate buffer of (layer, stage) aside during forward()
     // one-launch-per-token decode kernel (decode.cu)
+    unsigned long long *d_prof = nullptr;
     DecodeLayer *d_layers = nullptr; unsigned int *d_bar = nullptr; int *d_n_past = nullptr; int *h_n_past = nullptr;
-    float *qbuf = nullptr, *attn = nullptr;
+    float *qbuf = nullptr, *attn = nullptr; int4 *xpack_d = nullptr, *xpack_f = nullptr;
     int dev_n_past = -1;             // value currently held by *d_n_past (-1: unknown)
     bool mega_ok = false; int mega_grid = 0;
+    std::vector<DecodeLayer> h_layers;                 // host copy of the layer table (kernel arguments of the decode graph)
+    int4 *xpack_a = nullptr;
+    bool decode_warm = false;                          // first decode step runs eagerly (sets kernel attributes), later ones replay a graph
+    std::vector<std::pair<int, cudaGraphExec_t>> graphs;   // (n_kv bucket, instantiated graph)
+    int graph_nodes = 0;
     DecodeParams dp;
     int tap_layer = -2, tap_stage = 0;
     float *tap = nullptr; size_t tap_cap = 0, tap_count = 0;
@@ -100,8 +108,8 @@ bool b200_model::lookup(const char *name, Slot &s, int &slot_id) {
     if (!strcmp(sub, "attention.wk.weight")) { s.q = row_view(L.wqkv, e, gqa); slot_id = base + 3; return true; }
     if (!strcmp(sub, "attention.wv.weight")) { s.q = row_view(L.wqkv, e + gqa, gqa); slot_id = base + 4; return true; }
     if (!strcmp(sub, "attention.wo.weight")) { s.q = L.wo; slot_id = base + 5; return true; }
-    if (!strcmp(sub, "feed_forward.w1.weight")) { s.q = row_view(L.w13, 0, f); slot_id = base + 6; return true; }
-    if (!strcmp(sub, "feed_forward.w3.weight")) { s.q = row_view(L.w13, f, f); slot_id = base + 7; return true; }
+    if (!strcmp(sub, "feed_forward.w1.weight")) { s.q = L.w13; s.chunk = 32; s.row0 = 0;  s.stride = 64; s.rows = f; slot_id = base + 6; return true; }
+    if (!strcmp(sub, "feed_forward.w3.weight")) { s.q = L.w13; s.chunk = 32; s.row0 = 32; s.stride = 64; s.rows = f; slot_id = base + 7; return true; }
     if (!strcmp(sub, "feed_forward.w2.weight")) { s.q = L.w2; slot_id = base + 8; return true; }
     return false;
 }
@@ -143,17 +151,45 @@ void forward(b200_session *s, int n) {
     Launches L;
     const bool fast = (s->cfg.flags & B200_SESSION_FAST) != 0;
     if (n == 1 && s->mega_ok && !fast && !(s->cfg.flags & B200_SESSION_UNFUSED) && s->tap_layer == -2) {
-        // decode: the whole token in one persistent cooperative kernel (decode.cu)
-        if (s->dev_n_past != n_past) {
+        if (s->dev_n_past != n_past) {                 // after a prefill / rewind the device copy of n_past is stale
+            B200_CHECK(cudaStreamSynchronize(st));      // (the pinned staging word may still be in flight)
             *s->h_n_past = n_past;
             B200_CHECK(cudaMemcpyAsync(s->d_n_past, s->h_n_past, sizeof(int), cudaMemcpyHostToDevice, st));
         }
-        if (launch_decode(s->dp, hp.wtype, st, &s->mega_grid)) {
+        if (s->cfg.flags & B200_SESSION_MEGA) {
+            // experimental: the whole token in one persistent cooperative kernel (decode.cu)
+            if (launch_decode(s->dp, hp.wtype, st, &s->mega_grid)) {
+                s->dev_n_past = n_past + 1;
+                s->last_launches = 1; s->last_n = 1; s->n_past += 1;
+                return;
+            }
+            s->mega_ok = false;
+        } else {
+            // default: 8 fused kernels per layer, replayed from one CUDA graph per token (decode_ops.cu)
+            int bucket = ((n_kv + 255) / 256) * 256; if (bucket > n_ctx) bucket = n_ctx;
+            int nodes = 0;
+            if (!s->decode_warm || (s->cfg.flags & B200_SESSION_NO_GRAPH)) {
+                decode_ops_enqueue(s->dp, s->h_layers, hp.wtype, bucket, s->xpack_a, st, &nodes);
+                s->decode_warm = true; s->graph_nodes = nodes;
+            } else {
+                cudaGraphExec_t exec = nullptr;
+                for (auto &g : s->graphs) if (g.first == bucket) exec = g.second;
+                if (!exec) {
+                    cudaGraph_t graph;
+                    B200_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    decode_ops_enqueue(s->dp, s->h_layers, hp.wtype, bucket, s->xpack_a, st, &nodes);
+                    B200_CHECK(cudaStreamEndCapture(st, &graph));
+                    B200_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+                    B200_CHECK(cudaGraphDestroy(graph));
+                    s->graphs.emplace_back(bucket, exec);
+                    s->graph_nodes = nodes;
+                }
+                B200_CHECK(cudaGraphLaunch(exec, st));
+            }
             s->dev_n_past = n_past + 1;
-            s->last_launches = 1; s->last_n = 1; s->n_past += 1;
+            s->last_launches = s->graph_nodes; s->last_n = 1; s->n_past += 1;
             return;
         }
-        s->mega_ok = false;
     }
     int il = -1;
     auto TAP = [&](int stage, const float *buf, size_t count) {
@@ -222,12 +258,13 @@ void forward(b200_session *s, int n) {
 
 }  // namespace
 
-// silu(a)*b over rows laid out [a(f) | b(f)]
+// silu(a)*b over rows of [w1 x | w3 x] interleaved in 32-column pieces: h1[c] at (c/32)*64 + c%32, h3[c] 32 further
 __global__ void silu_mul_rows_kernel(const uint16_t *__restrict__ t, const float *__restrict__ h13, float *__restrict__ out, int64_t f, int64_t total) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t r = i / f, c = i - r * f;
-    const float a = h13[r * 2 * f + c], b = h13[r * 2 * f + f + c];
+    const int64_t o = r * 2 * f + (c >> 5) * 64 + (c & 31);
+    const float a = h13[o], b = h13[o + 32];
     out[i] = __fmul_rn(f16_bits_to_f32(__ldg(t + f32_to_f16_bits(a))), b);
 }
 void silu_mul_rows(const float *h13, float *out, int64_t f, int64_t n, cudaStream_t st) {
@@ -341,10 +378,15 @@ b200_model *b200_llama_new(const b200_llama_hparams *hp) {
 
 size_t b200_model_weight_bytes(b200_model *m) { return m ? m->weight_bytes : 0; }
 
+static size_t slot_bytes(const b200_model::Slot &s) {
+    if (!s.is_q) return (size_t)s.n * 4;
+    return (size_t)(s.chunk ? s.rows : s.q.N) * s.q.nb * ggml_block_bytes(s.q.type);
+}
+
 size_t b200_model_tensor_nbytes(b200_model *m, const char *name) {
     b200_model::Slot s; int id;
     if (!m || !m->lookup(name, s, id)) return 0;
-    return s.is_q ? (size_t)s.q.N * s.q.nb * ggml_block_bytes(s.q.type) : (size_t)s.n * 4;
+    return slot_bytes(s);
 }
 
 int b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const void *host_data, size_t nbytes) {
@@ -353,11 +395,16 @@ int b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const 
     if (!m->lookup(name, s, id)) return B200_ERR_UNKNOWN_TENSOR;
     Runtime &R = rt();
     if (s.is_q) {
-        if (type != s.q.type || nbytes != (size_t)s.q.N * s.q.nb * ggml_block_bytes(type)) return B200_ERR_TENSOR_SHAPE;
+        if (type != s.q.type || nbytes != slot_bytes(s)) return B200_ERR_TENSOR_SHAPE;
         R.op_arena.reset();
         void *raw = R.op_arena.get(nbytes, R.stream);
         B200_CHECK(cudaMemcpyAsync(raw, host_data, nbytes, cudaMemcpyHostToDevice, R.stream));
-        repack_weights(s.q, raw, R.stream);
+        if (!s.chunk) repack_weights(s.q, raw, R.stream);
+        else {
+            const size_t piece = (size_t)s.chunk * s.q.nb * ggml_block_bytes(type);
+            for (int64_t c = 0; c * s.chunk < s.rows; c++)
+                repack_weights(row_view(s.q, c * s.stride + s.row0, s.chunk), (const char *)raw + c * piece, R.stream);
+        }
         B200_CHECK(cudaStreamSynchronize(R.stream));
     } else {
         if (type != T_F32 || nbytes != (size_t)s.n * 4) return B200_ERR_TENSOR_SHAPE;
@@ -373,10 +420,15 @@ int b200_model_read_tensor(b200_model *m, const char *name, void *host_out, size
     if (!m->lookup(name, s, id)) return B200_ERR_UNKNOWN_TENSOR;
     Runtime &R = rt();
     if (s.is_q) {
-        if (nbytes != (size_t)s.q.N * s.q.nb * ggml_block_bytes(s.q.type)) return B200_ERR_TENSOR_SHAPE;
+        if (nbytes != slot_bytes(s)) return B200_ERR_TENSOR_SHAPE;
         R.op_arena.reset();
         void *raw = R.op_arena.get(nbytes, R.stream);
-        unpack_weights(s.q, raw, R.stream);
+        if (!s.chunk) unpack_weights(s.q, raw, R.stream);
+        else {
+            const size_t piece = (size_t)s.chunk * s.q.nb * ggml_block_bytes(s.q.type);
+            for (int64_t c = 0; c * s.chunk < s.rows; c++)
+                unpack_weights(row_view(s.q, c * s.stride + s.row0, s.chunk), (char *)raw + c * piece, R.stream);
+        }
         B200_CHECK(cudaMemcpyAsync(host_out, raw, nbytes, cudaMemcpyDeviceToHost, R.stream));
         B200_CHECK(cudaStreamSynchronize(R.stream));
     } else {
@@ -451,6 +503,7 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
             hl[il] = DecodeLayer{L.wqkv, L.wo, L.w13, L.w2, L.attention_norm, L.ffn_norm,
                                  s->memory_k + (size_t)il * n_ctx * gqa, s->memory_v + (size_t)il * n_ctx * gqa};
         }
+        s->h_layers = hl;
         B200_CHECK(cudaMalloc(&s->d_layers, hl.size() * sizeof(DecodeLayer)));
         B200_CHECK(cudaMemcpy(s->d_layers, hl.data(), hl.size() * sizeof(DecodeLayer), cudaMemcpyHostToDevice));
     }
@@ -463,6 +516,14 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     P.token = s->d_tokens; P.n_past = s->d_n_past;
     P.x = s->x; P.q = s->qbuf; P.kq = s->kq; P.attn = s->attn; P.ff = s->ff; P.h13 = s->h13; P.logits = s->logits;
     P.bar = s->d_bar;
+    B200_CHECK(cudaMalloc(&s->xpack_d, (e / QK) * 64));
+    B200_CHECK(cudaMalloc(&s->xpack_f, (f / QK) * 64));
+    P.xpack_d = s->xpack_d; P.xpack_f = s->xpack_f;
+    B200_CHECK(cudaMalloc(&s->xpack_a, (e / QK) * 64));
+    P.scratch_bytes = decode_scratch_bytes((int)e, (int)f, m->hd, (int)n_ctx);
+    B200_CHECK(cudaMalloc(&s->d_prof, 128 * sizeof(unsigned long long)));
+    B200_CHECK(cudaMemset(s->d_prof, 0, 128 * sizeof(unsigned long long)));
+    P.prof = getenv("B200_DECODE_PROF") ? s->d_prof : nullptr;
     s->mega_ok = hp.n_rot == m->hd && decode_supported(P, hp.wtype);
     return s;
 }
@@ -540,13 +601,21 @@ int64_t b200_session_read_tap(b200_session *s, float *host_out, int64_t max_coun
     return (int64_t)c;
 }
 
+int b200_session_decode_profile(b200_session *s, unsigned long long *out128) {
+    if (!s || !out128) return B200_ERR_BAD_ARG;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    B200_CHECK(cudaMemcpy(out128, s->d_prof, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
 int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchronize(rt().stream)); return B200_OK; }
 
 void b200_session_free(b200_session *s) {
     if (!s) return;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     if (s->h_n_past) B200_CHECK(cudaFreeHost(s->h_n_past));
-    void *dev[] = {s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack};
+    for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
+    void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
     if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));

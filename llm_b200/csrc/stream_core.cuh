@@ -8,7 +8,7 @@ namespace stream {
 
 constexpr int SR = 32;        // rows per tile
 constexpr int SCB = 16;       // quant blocks per ring stage
-constexpr int SST = 4;        // ring stages
+constexpr int SST = 4;        // ring stages of the stand-alone mat-vec kernel (the decode kernel uses a deeper ring: Ring::nst)
 constexpr int SCOMPUTE = 128; // 4 compute warps (4 threads per row)
 constexpr int STHREADS = SCOMPUTE + 32;   // + 1 producer warp
 
@@ -23,6 +23,7 @@ template <int TYPE> struct St {
     static constexpr int QS_BYTES = SR * QS_STRIDE, DM_BYTES = SR * DM_STRIDE, QH_BYTES = QH ? SR * QH_STRIDE : 0;
     static constexpr int STAGE_BYTES = QS_BYTES + DM_BYTES + QH_BYTES;
     static constexpr int RING_BYTES = SST * STAGE_BYTES;
+    __host__ __device__ static constexpr int ring_bytes(int nst) { return nst * STAGE_BYTES; }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -42,14 +43,16 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void *src) { asm volati
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SCOMPUTE) : "memory"); }   // the 4 compute warps only
 
+constexpr int SST_MAX = 8;
 struct Ring {                 // per-CTA streaming state (lives in registers; the storage is shared memory)
-    uint64_t *full, *empty;
+    uint64_t *full, *empty;   // [nst] each
     uint8_t *base;
     uint32_t g;               // running stage counter: producer and consumers enumerate stages in the same order
+    uint32_t nst;             // ring depth (<= SST_MAX)
 };
 
-__device__ __forceinline__ void ring_init(uint64_t *full, uint64_t *empty) {   // one thread, before a CTA-wide barrier
-    for (int s = 0; s < SST; s++) { mbar_init(&full[s], 32); mbar_init(&empty[s], SCOMPUTE / 32); }
+__device__ __forceinline__ void ring_init(uint64_t *full, uint64_t *empty, int nst) {   // one thread, before a CTA-wide barrier
+    for (int s = 0; s < nst; s++) { mbar_init(&full[s], 32); mbar_init(&empty[s], SCOMPUTE / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
@@ -77,18 +80,21 @@ __device__ __forceinline__ void stream_plane(uint32_t dst, int dst_pitch, const 
 }
 
 // Producer warp: stream every row tile (tile0, tile0 + tstride, ...) of W through the ring.
+// Tiles are handed out in groups of G consecutive tiles (G = 2 lets an epilogue see 64 consecutive rows, e.g. 32 rows of w1 and the
+// matching 32 rows of w3): group g = tile0, tile0 + tstride, ... covers tiles [g*G, g*G + G).
 template <int TYPE>
-__device__ __forceinline__ void produce_matvec(const QWeight &w, Ring &R, int tile0, int tstride, int lane) {
+__device__ __forceinline__ void produce_matvec(const QWeight &w, Ring &R, int tile0, int tstride, int lane, int G = 1) {
     using T = St<TYPE>;
     const int nb = (int)w.nb, nchunks = (nb + SCB - 1) / SCB, ntiles = (int)((w.N + SR - 1) / SR);
     const uint32_t ring_u32 = smem_u32(R.base);
-    for (int tile = tile0; tile < ntiles; tile += tstride) {
+    for (int grp = tile0; grp * G < ntiles; grp += tstride)
+    for (int tile = grp * G; tile < grp * G + G && tile < ntiles; tile++) {
         const int64_t row_base = (int64_t)tile * SR;
         const int rows_valid = (int)(w.N - row_base < SR ? w.N - row_base : SR);
         for (int c = 0; c < nchunks; c++, R.g++) {
-            const int s = R.g % SST;
+            const int s = R.g % R.nst;
             const int b0 = c * SCB, cb = nb - b0 < SCB ? nb - b0 : SCB;
-            mbar_wait(&R.empty[s], ((R.g / SST) & 1) ^ 1);
+            mbar_wait(&R.empty[s], ((R.g / R.nst) & 1) ^ 1);
             const uint32_t st = ring_u32 + s * T::STAGE_BYTES;
             stream_plane<SCB * T::QS / 16>(st, T::QS_STRIDE, w.qs + (row_base * nb + b0) * T::QS, (int64_t)nb * T::QS, cb * T::QS / 16, rows_valid, lane);
             stream_plane<SCB * T::DM / 16>(st + T::QS_BYTES, T::DM_STRIDE, (const uint8_t *)w.dm + (row_base * nb + b0) * T::DM, (int64_t)nb * T::DM,
@@ -104,16 +110,17 @@ __device__ __forceinline__ void produce_matvec(const QWeight &w, Ring &R, int ti
 // Compute warps: walk the AVX2 lane chains of the tiles this CTA owns.  epi(row, value) is called by ALL 128 threads once per tile
 // (value = the finished dot product of `row`, identical in the 4 threads of a quad; row may be >= w.N on the tail tile).
 template <int TYPE, class Epi>
-__device__ __forceinline__ void consume_matvec(const QWeight &w, const int4 *sx, Ring &R, int tile0, int tstride, int tid, Epi epi) {
+__device__ __forceinline__ void consume_matvec(const QWeight &w, const int4 *sx, Ring &R, int tile0, int tstride, int tid, Epi epi, int G = 1) {
     using T = St<TYPE>;
     const int nb = (int)w.nb, nchunks = (nb + SCB - 1) / SCB, ntiles = (int)((w.N + SR - 1) / SR);
     const int r = tid >> 2, wd = tid & 3, lane = tid & 31;
-    for (int tile = tile0; tile < ntiles; tile += tstride) {
+    for (int grp = tile0; grp * G < ntiles; grp += tstride)
+    for (int tile = grp * G; tile < grp * G + G && tile < ntiles; tile++) {
         float a_lo = 0.f, a_hi = 0.f, summs = 0.f;
         for (int c = 0; c < nchunks; c++, R.g++) {
-            const int s = R.g % SST;
+            const int s = R.g % R.nst;
             const int b0 = c * SCB, cb = nb - b0 < SCB ? nb - b0 : SCB;
-            mbar_wait(&R.full[s], (R.g / SST) & 1);
+            mbar_wait(&R.full[s], (R.g / R.nst) & 1);
             const uint8_t *st = R.base + s * T::STAGE_BYTES;
             const uint8_t *qrow = st + r * T::QS_STRIDE, *drow = st + T::QS_BYTES + r * T::DM_STRIDE, *hrow = st + T::QS_BYTES + T::DM_BYTES + r * T::QH_STRIDE;
 #pragma unroll 8
@@ -190,6 +197,38 @@ __device__ __forceinline__ void pack_block(float v, int4 *rec4, int lane, int q8
             rec.w = __float_as_int(scale16 ? dx * 0.0625f : dx);
         }
         rec4[lane >> 2] = rec;
+    }
+}
+
+// Same arithmetic, 4 blocks per warp pass: lane l owns word (l & 7) = elements 4*(l&7) .. +3 of block (l >> 3).  The block maximum and
+// the quant sum need 3 xor-shuffles each inside the 8-lane group, the packed word and its byte sum are lane-local, and the record's
+// second word comes from 4 lanes up: 8 shuffles per 4 blocks instead of 16 per block.  `active` = this lane's block exists.
+__device__ __forceinline__ void pack_quad(float4 v, int4 *rec4_of_my_block, int lane, bool active, int q81, int off, int scale16) {
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+    const float d = __fdiv_rn(amax, 127.f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+    const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
+    const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
+    const uint32_t word = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+    const int s4 = q0 + q1 + q2 + q3;
+    int isum = s4 + __shfl_xor_sync(0xffffffffu, s4, 1);
+    isum += __shfl_xor_sync(0xffffffffu, isum, 2);
+    isum += __shfl_xor_sync(0xffffffffu, isum, 4);
+    const uint32_t word_hi = __shfl_down_sync(0xffffffffu, word, 4);
+    const int s4_hi = __shfl_down_sync(0xffffffffu, s4, 4);
+    if (active && (lane & 7) < 4) {
+        int4 rec;
+        rec.x = (int)word; rec.y = (int)word_hi;
+        if (q81) { rec.z = __float_as_int(__fmul_rn(d, (float)isum)); rec.w = __float_as_int(d); }
+        else {
+            rec.z = (int)(((uint32_t)(-off * s4) & 0xffffu) | ((uint32_t)(-off * s4_hi) << 16));
+            const float dx = __half2float(__float2half_rn(d));
+            rec.w = __float_as_int(scale16 ? dx * 0.0625f : dx);
+        }
+        rec4_of_my_block[lane & 7] = rec;
     }
 }
 

@@ -14,7 +14,7 @@ CONFIGS = {
     "tiny":   dict(n_vocab=320, n_embd=256, n_head=4, n_head_kv=4, n_layer=2, n_ff=704, n_rot=64, n_ctx=128),
     # shapes the one-launch decode kernel accepts (K % 256 == 0), incl. grouped-query attention
     "tiny8":  dict(n_vocab=320, n_embd=256, n_head=4, n_head_kv=4, n_layer=2, n_ff=768, n_rot=64, n_ctx=128),
-    "gqa8":   dict(n_vocab=352, n_embd=512, n_head=8, n_head_kv=2, n_layer=3, n_ff=1024, n_rot=64, n_ctx=160),
+    "gqa8":   dict(n_vocab=352, n_embd=512, n_head=8, n_head_kv=2, n_layer=3, n_ff=1024, n_rot=64, n_ctx=256),
     "small":  dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=8, n_layer=3, n_ff=1408, n_rot=64, n_ctx=256),
     # 7B layer geometry with few layers (BASELINE.json configs[1]/[2] shapes)
     "7b-2l":  dict(n_vocab=32000, n_embd=4096, n_head=32, n_head_kv=32, n_layer=2, n_ff=11008, n_rot=128, n_ctx=1024),

@@ -5,6 +5,10 @@ import sys
 import numpy as np
 import pytest
 
+# the oracle's OpenMP loops are tiny; 128 threads per process under pytest-xdist oversubscribes the GPU box's host badly
+os.environ.setdefault("OMP_NUM_THREADS", "8")
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
