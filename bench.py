@@ -5,7 +5,9 @@
   python bench.py --impl reference [...]                        the reference's own ggml CPU path on the host cores
 
 A "step" is one pass of the hot path over one batch: one decode token (Llama::evaluate with 1 token) at n_past = 512 on a
-synthetic, device-generated LLaMA-7B Q4_0 model (BASELINE.json configs[1]).  `value` is measured with inputs resident in
+synthetic, device-generated LLaMA-7B Q4_0 model (BASELINE.json configs[1]).  Every headline number is measured on the CONFORMANT
+path: kernels that reproduce the reference's AVX2 operation order, logits bit-identical to the reference CPU path.
+The order-free kernels (B200_SESSION_FAST) are reported beside it under "fast_mode" and labelled non-conformant.  `value` is measured with inputs resident in
 HBM (token id and logits stay on the device); `e2e` goes through the host-buffer call (b200_session_evaluate: token H2D,
 logits D2H, sync) every step.  Timing: CUDA events on the backend's stream, W >= 3 warm-up steps, the 3.7 GB of weights
 are far larger than the 126 MB L2 so every step streams them from HBM.  Multi-GPU (the path does not need to shard: 7B fits
@@ -230,8 +232,38 @@ def main():
         pk = peaks()
         prefill = {"value": N_PAST / (ms * 1e-3), "unit": "tokens/s", "ms": ms, "reps": reps, "launches": pf_launches,
                    "tensor_frac_of_bf16_sustained": fl / (ms * 1e-3) / (pk["bf16_sustained"] * 1e12),
-                   "note": "integer-exact (conformant) path: int8 MMA per quant block + fp32 scale-accumulate; includes attention and the 2 KB token upload"}
+                   "note": "conformant (bit-exact) path: AVX2-order lane chains on dp4a; includes attention and the 2 KB token upload"}
         log(f"prefill@512: {ms:.2f} ms -> {prefill['value']:.0f} tok/s ({pf_launches} kernels)")
+
+    # ---- non-conformant fast mode (order-free kernels), reported separately ----
+    fast_mode = None
+    if not args.no_prefill and world == 1:
+        fs = model.start_session(llm_b200.InferenceSessionConfig(n_batch=512, flags=4))
+        tokp = np.ascontiguousarray(prompt[:N_PAST])
+        fms = []
+        for r in range(4):
+            fs.rewind(0)
+            L.b200_timing_begin()
+            assert L.b200_session_evaluate(fs._s, tokp.ctypes.data, N_PAST, None, 0) == 0
+            fms.append(L.b200_timing_end_ms())
+        f_pf = statistics.median(fms[1:])
+        onef = np.ascontiguousarray(prompt[N_PAST:N_PAST + 1])
+        assert L.b200_session_evaluate(fs._s, onef.ctypes.data, 1, None, 0) == 0
+        f_launch = fs.last_launches
+        for _ in range(warmup):
+            fs.rewind(N_PAST); L.b200_session_evaluate_device(fs._s, None, 1)
+        L.b200_timing_begin()
+        for _ in range(steps):
+            fs.rewind(N_PAST); L.b200_session_evaluate_device(fs._s, None, 1)
+        f_dec = L.b200_timing_end_ms() / steps
+        fl = prefill_flops(hp, N_PAST)
+        fast_mode = {"conformant": False,
+                     "note": "integer-exact block dots, free f32 summation order: <=2e-6 per mat-mul, ~1e-2 on logits (the reference's own sensitivity to re-association, tests/test_chaos.py)",
+                     "decode_tokens_per_s": 1e3 / f_dec, "decode_ms": f_dec, "decode_launches": f_launch,
+                     "prefill_tokens_per_s": N_PAST / (f_pf * 1e-3), "prefill_ms": f_pf,
+                     "prefill_tensor_frac_of_bf16_sustained": fl / (f_pf * 1e-3) / (peaks()["bf16_sustained"] * 1e12)}
+        log(f"fast mode (non-conformant): decode {1e3 / f_dec:.0f} tok/s, prefill@512 {f_pf:.2f} ms")
+        fs.close()
 
     # decode@1 at n_past = 512: device-resident arm
     one = np.ascontiguousarray(prompt[N_PAST:N_PAST + 1])
@@ -289,7 +321,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8xint8->f32 (Q4_0 x Q8_0 blocks)", "data": "synthetic",
+        "dtype": "u8/s8 block dots -> f32 (Q4_0 weights x Q8_0 activations)", "data": "synthetic",
         "config": {"workload": "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1])", "n_layer": hp["n_layer"], "n_ctx": 2048,
                    "kv_cache": "f16", "parallelism": f"{world} independent replica(s), no collective",
                    "l2": "inputs larger than L2: 3.7 GB of weights streamed per step vs 126 MB L2",
@@ -297,7 +329,7 @@ def main():
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 * hp["n_vocab"], "ms_per_step": ms_e2e / steps},
         "gpu_launches": launches_per_step * steps,
         "launches_per_step": launches_per_step,
-        "roofline": {"bound": "hbm", "kernel": "mmvq_kernel<Q4_0> (all 129 weight mat-vecs of the model, timed alone)",
+        "roofline": {"bound": "hbm", "kernel": "mmv_exact_stream_kernel<Q4_0>: all 129 weight mat-vecs of the model back to back, timed alone (the dominant kernel: 93% of a token's bytes)",
                      "achieved": probe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": probe_gbs / pk["hbm_gbs"], "peak_source": pk["source"] + " (burst copy)",
                      "traffic": None, "launches": int(nl.value), "avg_launch_us": ms_probe * 1e3 / max(1, nl.value),
                      "algorithmic_bytes_per_launch": nbytes.value / max(1, nl.value)},
@@ -305,8 +337,11 @@ def main():
                           "frac": tok_bytes / (ms_dev / steps * 1e-3) / 1e9 / pk["hbm_gbs"]},
         "clocks": clocks,
     }
+    line["conformance"] = "logits bit-identical to the reference ggml CPU path (tests/test_gpu_llama.py); decode schedule: 8 fused kernels/layer replayed from one CUDA graph"
     if prefill:
         line["prefill"] = prefill
+    if fast_mode:
+        line["fast_mode"] = fast_mode
     if not args.no_cpu_baseline and world == 1:
         try:
             cb = cpu_reference_decode(6, 2, log=log)
