@@ -129,36 +129,38 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
     }
 }
 
-// ---- 3: KQ.  CTA = (64 cached positions, head); CTAs past n_kv exit at once (the grid is sized for the context bucket). ----------------
+// ---- 3: KQ.  CTA = (64 cached positions, head); CTAs past n_kv exit at once (the grid is sized for the context bucket).  All
+//      16-byte loads of the K tile are issued before the first one is consumed. ---------------------------------------------------------
+template <int HD>
 __global__ void __launch_bounds__(128) attn_kq_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, float *__restrict__ kq,
-                                                      const int *__restrict__ n_past, int hd, int gqa, int n_head, int n_head_kv, int n_ctx) {
-    extern __shared__ __align__(16) uint8_t sm[];
+                                                      const int *__restrict__ n_past, int gqa, int n_head, int n_head_kv, int n_ctx) {
+    __shared__ __align__(16) __half q16[HD];
+    __shared__ __align__(16) __half kt[64 * HD];
     const int n_kv = __ldg(n_past) + 1;
     const int j0 = blockIdx.x * 64, h = blockIdx.y;
     if (j0 >= n_kv) return;
-    __half *q16 = (__half *)sm;
-    __half *kt = (__half *)(sm + 512);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hk = h / (n_head / n_head_kv);
     const int rows = n_kv - j0 < 64 ? n_kv - j0 : 64;
-    const int vec_per_row = hd / 8;
-    for (int i = tid; i < hd; i += 128) q16[i] = __float2half_rn(q[h * hd + i]);
-    for (int i = tid; i < rows * vec_per_row; i += 128) {
-        const int rr = i / vec_per_row, cc = i - rr * vec_per_row;
-        ((int4 *)kt)[rr * vec_per_row + cc] = __ldg((const int4 *)(Kl + (int64_t)(j0 + rr) * gqa + hk * hd) + cc);
+    constexpr int VPR = HD / 8;                       // 16-byte vectors per K row
+    constexpr int NV = 64 * VPR / 128;                // vectors per thread
+    int4 v[NV];
+#pragma unroll
+    for (int u = 0; u < NV; u++) {
+        const int i = tid + u * 128, rr = i / VPR, cc = i % VPR;
+        v[u] = rr < rows ? __ldg((const int4 *)(Kl + (int64_t)(j0 + rr) * gqa + hk * HD) + cc) : make_int4(0, 0, 0, 0);
     }
+    for (int i = tid; i < HD; i += 128) q16[i] = __float2half_rn(q[h * HD + i]);
+#pragma unroll
+    for (int u = 0; u < NV; u++) ((int4 *)kt)[tid + u * 128] = v[u];
     __syncthreads();
-    const int np = hd & ~31;
     for (int jj = warp; jj < rows; jj += 4) {
-        const __half *krow = kt + jj * hd;
+        const __half *krow = kt + jj * HD;
         float s = 0.f;
-        for (int k = lane; k < np; k += 32) s = __fmaf_rn(__half2float(krow[k]), __half2float(q16[k]), s);
+#pragma unroll
+        for (int k = 0; k < HD; k += 32) s = __fmaf_rn(__half2float(krow[k + lane]), __half2float(q16[k + lane]), s);
         s = f16dot_tree(s);
-        if (lane == 0) {
-            double sumf = (double)s;
-            for (int k = np; k < hd; k++) sumf += (double)__fmul_rn(__half2float(krow[k]), __half2float(q16[k]));
-            kq[(int64_t)h * n_ctx + j0 + jj] = (float)sumf;
-        }
+        if (lane == 0) kq[(int64_t)h * n_ctx + j0 + jj] = (float)(double)s;
     }
 }
 
@@ -178,23 +180,8 @@ __global__ void __launch_bounds__(128) attn_sv_kernel(const float *__restrict__ 
     __half *p16 = (__half *)(sm + (size_t)n_ctx * 4);
     __half *vt = (__half *)(sm + (size_t)n_ctx * 6);
     __half *vleft = vt + 32 * KC;
-    float mx = -INFINITY;
-    for (int j = tid; j < n_kv; j += 128) { const float v = __fmul_rn(kq[(int64_t)h * n_ctx + j], kq_scale); sc[j] = v; mx = fmaxf(mx, v); }
-    mx = warp_max(mx);
-    if (lane == 0) shf[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(shf[0], shf[1]), fmaxf(shf[2], shf[3]));
-    double s = 0.0;
-    for (int j = tid; j < n_kv; j += 128) { const float ev = lutf(lut_exp, __fsub_rn(sc[j], mx)); sc[j] = ev; s += (double)ev; }
-    s = warp_sum(s);
-    if (lane == 0) shd[warp] = s;
-    __syncthreads();
-    const float inv = (float)(1.0 / ((shd[0] + shd[1]) + (shd[2] + shd[3])));
-    for (int j = tid; j < n_kv; j += 128) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
+    // leftover V columns and the first V tile are requested before anything else so that their latency hides behind the soft_max
     const int np = n_kv & ~31;
-    float acc[8];
-#pragma unroll
-    for (int cc = 0; cc < 8; cc++) acc[cc] = 0.f;
     if (np < n_kv) {
         const int rr = tid >> 2, part = tid & 3;
         ((int4 *)vleft)[tid] = __ldg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + np) + part);
@@ -208,6 +195,35 @@ __global__ void __launch_bounds__(128) attn_sv_kernel(const float *__restrict__ 
         }
     };
     if (np > 0) fetch(0);
+    float mx = -INFINITY;
+    constexpr int SB = 8;                              // scores per thread per pass: 8 loads in flight
+    for (int jb = 0; jb < n_kv; jb += SB * 128) {
+        float sv[SB];
+#pragma unroll
+        for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; sv[u] = j < n_kv ? kq[(int64_t)h * n_ctx + j] : 0.f; }
+#pragma unroll
+        for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; if (j < n_kv) { const float v = __fmul_rn(sv[u], kq_scale); sc[j] = v; mx = fmaxf(mx, v); } }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) shf[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(shf[0], shf[1]), fmaxf(shf[2], shf[3]));
+    double s = 0.0;
+    for (int jb = 0; jb < n_kv; jb += SB * 128) {
+        uint16_t ev16[SB];
+#pragma unroll
+        for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; ev16[u] = j < n_kv ? __ldg(lut_exp + f32_to_f16_bits(__fsub_rn(sc[j], mx))) : (uint16_t)0; }
+#pragma unroll
+        for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; if (j < n_kv) { const float ev = f16_bits_to_f32(ev16[u]); sc[j] = ev; s += (double)ev; } }
+    }
+    s = warp_sum(s);
+    if (lane == 0) shd[warp] = s;
+    __syncthreads();
+    const float inv = (float)(1.0 / ((shd[0] + shd[1]) + (shd[2] + shd[3])));
+    for (int j = tid; j < n_kv; j += 128) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
+    float acc[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; cc++) acc[cc] = 0.f;
     for (int k0 = 0; k0 < np; k0 += KC) {
         __syncthreads();
 #pragma unroll
@@ -261,7 +277,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     const int e = P.e, f = P.f;
     int n = 0;
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
-    const size_t kq_smem = 512 + (size_t)64 * P.hd * 2, sv_smem = (size_t)P.n_ctx * 6 + 32 * KC * 2 + 32 * 32 * 2;
+    const size_t sv_smem = (size_t)P.n_ctx * 6 + 32 * KC * 2 + 32 * 32 * 2;
     static size_t sv_set = 48 * 1024;
     if (sv_smem > sv_set) { B200_CHECK(cudaFuncSetAttribute(attn_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem)); sv_set = sv_smem; }
     for (int il = 0; il < P.n_layer; il++) {
@@ -270,7 +286,9 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
         MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
         launch_mmv<TYPE, EPI_QKV>(L.wqkv, A, st); n++;
-        attn_kq_kernel<<<dim3((n_kv_bucket + 63) / 64, P.n_head), 128, kq_smem, st>>>(P.q, L.K, P.kq, P.n_past, P.hd, P.gqa, P.n_head, P.n_head_kv, P.n_ctx); n++;
+        if (P.hd == 128) attn_kq_kernel<128><<<dim3((n_kv_bucket + 63) / 64, P.n_head), 128, 0, st>>>(P.q, L.K, P.kq, P.n_past, P.gqa, P.n_head, P.n_head_kv, P.n_ctx);
+        else             attn_kq_kernel<64><<<dim3((n_kv_bucket + 63) / 64, P.n_head), 128, 0, st>>>(P.q, L.K, P.kq, P.n_past, P.gqa, P.n_head, P.n_head_kv, P.n_ctx);
+        n++;
         attn_sv_kernel<<<P.n_head * (P.hd / 32), 128, sv_smem, st>>>(P.kq, L.V, P.xpack_d, P.n_past, P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.n_ctx,
                                                                       q81, off, s16); n++;
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;

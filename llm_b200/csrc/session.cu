@@ -524,7 +524,7 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMalloc(&s->d_prof, 128 * sizeof(unsigned long long)));
     B200_CHECK(cudaMemset(s->d_prof, 0, 128 * sizeof(unsigned long long)));
     P.prof = getenv("B200_DECODE_PROF") ? s->d_prof : nullptr;
-    s->mega_ok = hp.n_rot == m->hd && decode_supported(P, hp.wtype);
+    s->mega_ok = hp.n_rot == m->hd && (m->hd == 64 || m->hd == 128) && decode_supported(P, hp.wtype);
     return s;
 }
 
