@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
     if (tid == 0) ring_init(R.full, R.empty, SST);
     __syncthreads();
     if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31, G); return; }
-    for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) sx[i] = __ldg(A.xpack + i);
+    for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
+    asm volatile("cp.async.wait_all;" ::: "memory");
     float *stash = (float *)(sx + (size_t)w.nb * 4);      // 64 floats behind the records (EPI_SILU)
     compute_sync();
     const int lane = tid & 31, warp = tid >> 5;

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(STHREADS) mmv_exact_stream_kernel(const QWeigh
     if (tid == 0) ring_init(R.full, R.empty, SST);
     __syncthreads();
     if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31); return; }
-    for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) sx[i] = __ldg(xpack + i);
+    for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), xpack + i);     // all 16-byte copies in flight at once
+    asm volatile("cp.async.wait_all;" ::: "memory");
     compute_sync();
     consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
         if ((tid & 3) == 0 && row < w.N) dst[row] = addend ? __fadd_rn(v, addend[row]) : v;

@@ -37,6 +37,10 @@ void mul_mat_q_simple(const QWeight &w, const int8_t *xq, const float2 *xds, flo
 // same contract as mul_mat_q for any B >= 1; results are bit-identical to ggml_compute_forward_mul_mat on the reference's x86 build
 void mul_mat_q_exact(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 
+// ---- exact_mma.cu : bit-exact batched mat-mul with the block dots on tensor cores (block-diagonal f16 MMA) --------------------------
+void quantize_act_f16(int vdt, const float *x, int64_t ldx, __half *xh, float2 *ds, int64_t K, int64_t B, cudaStream_t st);
+void mul_mat_q_exact_mma(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
+
 // ---- exact_stream.cu : the bit-exact decode mat-vec at HBM speed (TMA bulk-copy ring + AVX2 lane chains) ----------------------------
 bool mmv_exact_stream_supported(const QWeight &w);
 // bit-faithful activation quantizer emitting 16-byte records per (block, word): see exact_stream.cu

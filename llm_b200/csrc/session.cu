@@ -68,7 +68,7 @@ struct b200_session {
     // activations (sized for n_batch rows)
     int32_t *d_tokens = nullptr;
     float *x = nullptr, *cur = nullptr, *ff = nullptr, *qkv = nullptr, *kq = nullptr, *h13 = nullptr, *hmul = nullptr, *logits = nullptr;
-    int8_t *xq = nullptr; float2 *xds = nullptr; int4 *xpack = nullptr;
+    int8_t *xq = nullptr; float2 *xds = nullptr; int4 *xpack = nullptr; __half *xh = nullptr;
     // pinned host staging
     int32_t *h_tokens = nullptr; float *h_logits = nullptr;
     cudaEvent_t tokens_uploaded = nullptr;   // guards reuse of h_tokens by the next evaluate()
@@ -128,6 +128,12 @@ void matmul(b200_session *s, const QWeight &w, const float *x, float *dst, int64
     if (B == 1 && !fast && mmv_exact_stream_supported(w)) {
         quantize_act_pack(w.type, x, s->xpack, w.K, st);
         mul_mat_vec_q_exact_stream(w, s->xpack, dst, addend, st);
+        L.n += 2;
+        return;
+    }
+    if (!fast && B >= 16) {                          // prefill: bit-exact, block dots on tensor cores (exact_mma.cu)
+        quantize_act_f16(vec_dot_type(w.type), x, w.K, s->xh, s->xds, w.K, B, st);
+        mul_mat_q_exact_mma(w, s->xh, s->xds, dst, ldd, B, addend, lda, st);
         L.n += 2;
         return;
     }
@@ -485,6 +491,7 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMalloc(&s->xq, B * kmax));
     B200_CHECK(cudaMalloc(&s->xds, B * (kmax / QK) * sizeof(float2)));
     B200_CHECK(cudaMalloc(&s->xpack, (kmax / QK) * 64));
+    B200_CHECK(cudaMalloc(&s->xh, B * kmax * 2));
     B200_CHECK(cudaMallocHost(&s->h_tokens, B * 4));
     B200_CHECK(cudaMallocHost(&s->h_logits, B * (size_t)hp.n_vocab * 4));
     B200_CHECK(cudaEventCreateWithFlags(&s->tokens_uploaded, cudaEventDisableTiming));
@@ -615,7 +622,7 @@ void b200_session_free(b200_session *s) {
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     if (s->h_n_past) B200_CHECK(cudaFreeHost(s->h_n_past));
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
-    void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack};
+    void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack, s->xh};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
     if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));
@@ -660,7 +667,11 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
     B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
     quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
     if (impl == B200_MM_AUTO) impl = B200_MM_EXACT;
-    if (impl == B200_MM_EXACT_STREAM) {
+    if (impl == B200_MM_EXACT_MMA) {
+        __half *xh = (__half *)R.op_arena.get((size_t)B * K * 2, st);
+        quantize_act_f16(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
+        mul_mat_q_exact_mma(w, xh, xds, dd, N, B, nullptr, 0, st);
+    } else if (impl == B200_MM_EXACT_STREAM) {
         if (!mmv_exact_stream_supported(w)) return B200_ERR_BAD_ARG;
         int4 *pack = (int4 *)R.op_arena.get((size_t)(K / QK) * 64, st);
         for (int64_t b = 0; b < B; b++) { quantize_act_pack(wtype, dx + b * K, pack, K, st); mul_mat_vec_q_exact_stream(w, pack, dd + b * N, nullptr, st); }
