@@ -4,6 +4,10 @@
 
 #include "kernels.cuh"
 
+#ifndef B200_PROF_SLOTS
+#define B200_PROF_SLOTS 1024
+#endif
+
 namespace b200 {
 
 struct DecodeLayer {
@@ -27,7 +31,7 @@ struct DecodeParams {
     int scratch_bytes;                  // decode_scratch_bytes(): per-CTA shared memory behind the weight ring
     int4 *xpack_d, *xpack_f;            // activation records produced by phase C (for wo) and phase E (for w2)
     unsigned int *bar;                  // [0] arrival count, [1] generation
-    unsigned long long *prof;           // optional: %globaltimer stamps of CTA 0 at phase boundaries (debug / tuning), 128 slots
+    unsigned long long *prof;   /* graph schedule: 3 x B200_PROF_SLOTS timeline slots (begin | end | prologue done) */           // optional: %globaltimer stamps of CTA 0 at phase boundaries (debug / tuning), 128 slots
 };
 
 int decode_scratch_bytes(int e, int f, int hd, int n_ctx);

@@ -10,6 +10,11 @@
 //   8 mmv<RES>         w2 h + inpFF                                                           (:332-334)
 // Everything that depends on the position reads n_past from DEVICE memory, so the captured graph is valid for every token; the
 // last node increments it.  All arithmetic is the bit-exact arithmetic of exact.cu / rowops.cu (same device functions as decode.cu).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include <array>
+#include <map>
 #include <vector>
 
 #include "decode.h"
@@ -20,6 +25,37 @@ namespace b200 {
 using namespace stream;
 
 namespace {
+
+// Programmatic dependent launch: every kernel of the chain lets its successor start launching at once (`pdl_trigger`) and touches nothing
+// a predecessor writes (and writes nothing at all) before `pdl_wait`.  What runs ahead of the wait is the part that only reads the constant
+// weights: the producer warp of the next mat-vec fills its ring while the previous kernels drain, so HBM stays busy across kernel boundaries.
+// tuning aid: per-launch timeline (DecodeParams::prof), see b200_session_decode_timeline
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void prof_begin(unsigned long long *p) { if (p && threadIdx.x == 0) { const unsigned long long t = gtime(); atomicMin(p, t); atomicMax(p + 3 * B200_PROF_SLOTS, t); } }
+__device__ __forceinline__ void prof_ready(unsigned long long *p) { if (p && threadIdx.x == 0) { const unsigned long long t = gtime(); atomicMin(p + 2 * B200_PROF_SLOTS, t); atomicMax(p + 4 * B200_PROF_SLOTS, t); } }
+__device__ __forceinline__ void prof_end(unsigned long long *p) { if (p && threadIdx.x == 0) atomicMax(p + B200_PROF_SLOTS, gtime()); }
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Measured on B200 (r01e): programmatic edges cost more than they hide here (2.02 -> 2.11 ms/token with bit 0, 2.41 with both), so the default is off.
+// B200_PDL: bit 0 = the weight mat-vecs are launched as programmatic dependents, bit 1 = the small kernels between them too
+int pdl_mask() {
+    static int mask = -1;
+    if (mask < 0) { const char *e = getenv("B200_PDL"); mask = e ? atoi(e) : 0; }
+    return mask;
+}
+
+template <int CLASS = 2, typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & CLASS) ? 1 : 0;
+    B200_CHECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
 
 __device__ __forceinline__ float lutf(const uint16_t *t, float x) { return f16_bits_to_f32(__ldg(t + f32_to_f16_bits(x))); }
 __device__ __forceinline__ float f16dot_tree(float s) {          // ggml_vec_dot_f16 reduction order, see exact.cu
@@ -34,12 +70,15 @@ __device__ __forceinline__ float f16dot_tree(float s) {          // ggml_vec_dot
 // ---- 1 / 6: rms_norm * gain -> records.  grid = e/128 CTAs of 256 threads; every CTA reduces the whole row (16 KB from L2) and
 //      quantizes its own 4 blocks per warp pass. ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
-                                                        int e, float eps, int q81, int off, int scale16) {
+                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof) {
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
+    prof_begin(prof);
     double s = 0.0;
     for (int i = tid; i < e / 4; i += 256) {
-        const float4 v = __ldg((const float4 *)x + i);
+        const float4 v = __ldcg((const float4 *)x + i);                       // written by a predecessor: L2-coherent load
         s += (double)__fmul_rn(v.x, v.x); s += (double)__fmul_rn(v.y, v.y); s += (double)__fmul_rn(v.z, v.z); s += (double)__fmul_rn(v.w, v.w);
     }
     s = warp_sum(s);
@@ -53,11 +92,12 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     const bool active = b < e / QK;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
-        const float4 xv = __ldg((const float4 *)x + b * 8 + (lane & 7)), gv = __ldg((const float4 *)gain + b * 8 + (lane & 7));
+        const float4 xv = __ldcg((const float4 *)x + b * 8 + (lane & 7)), gv = __ldg((const float4 *)gain + b * 8 + (lane & 7));
         v.x = __fmul_rn(__fmul_rn(xv.x, scale), gv.x); v.y = __fmul_rn(__fmul_rn(xv.y, scale), gv.y);
         v.z = __fmul_rn(__fmul_rn(xv.z, scale), gv.z); v.w = __fmul_rn(__fmul_rn(xv.w, scale), gv.w);
     }
     pack_quad(v, pack + (active ? b : 0) * 4, lane, active, q81, off, scale16);
+    prof_end(prof);
 }
 
 // ---- mat-vec with fused epilogues --------------------------------------------------------------------------------------------------
@@ -72,31 +112,37 @@ struct MmvArgs {
     int4 *xpack_out; const uint16_t *lut_silu;
     int q81, off, scale16;
     int *n_past_inc;              // EPI_LOGITS: the last node of the token increments InferenceSession::n_past on the device
+    int nst;                      // ring depth chosen by launch_mmv
+    unsigned long long *prof;
 };
 
 template <int TYPE, int EPI>
 __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, const MmvArgs A) {
     using T = St<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
-    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST_MAX, smem + 256, 0u, SST};
-    int4 *sx = (int4 *)(R.base + T::RING_BYTES);
+    Ring R{(uint64_t *)smem, (uint64_t *)smem + SST_MAX, smem + 256, 0u, (uint32_t)A.nst};
+    int4 *sx = (int4 *)(R.base + T::ring_bytes(A.nst));
     const int tid = threadIdx.x;
     constexpr int G = EPI == EPI_SILU ? 2 : 1;
-    if (tid == 0) ring_init(R.full, R.empty, SST);
+    prof_begin(A.prof);
+    if (tid == 0) ring_init(R.full, R.empty, A.nst);
+    pdl_trigger();
     __syncthreads();
-    if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31, G); return; }
+    if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31, G); return; }   // weights only: runs ahead of the predecessors
+    pdl_wait();
     for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
     asm volatile("cp.async.wait_all;" ::: "memory");
     float *stash = (float *)(sx + (size_t)w.nb * 4);      // 64 floats behind the records (EPI_SILU)
     compute_sync();
+    prof_ready(A.prof);
     const int lane = tid & 31, warp = tid >> 5;
     if (EPI == EPI_RES || EPI == EPI_LOGITS) {
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
-            if ((tid & 3) == 0 && row < w.N) A.dst[row] = A.addend ? __fadd_rn(v, A.addend[row]) : v;
-        });
+            if ((tid & 3) == 0 && row < w.N) A.dst[row] = A.addend ? __fadd_rn(v, __ldcg(A.addend + row)) : v;
+        }, 1, A.prof);
         if (EPI == EPI_LOGITS && blockIdx.x == 0 && tid == 0) *A.n_past_inc = *A.n_past_inc + 1;
     } else if (EPI == EPI_QKV) {
-        const int p = __ldg(A.n_past);
+        const int p = __ldcg(A.n_past);
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
             const float other = __shfl_xor_sync(0xffffffffu, v, 4);              // rotation partner: rows 2i, 2i+1 sit in adjacent quads
             if ((tid & 3) != 0 || row >= w.N) return;
@@ -126,18 +172,22 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
                 pack_quad(hm, A.xpack_out + (row >> 6) * 4, lane, lane < 8, A.q81, A.off, A.scale16);
             }
             compute_sync();
-        }, G);
+        }, G, A.prof);
     }
+    prof_end(A.prof);
 }
 
 // ---- 3: KQ.  CTA = (64 cached positions, head); CTAs past n_kv exit at once (the grid is sized for the context bucket).  All
 //      16-byte loads of the K tile are issued before the first one is consumed. ---------------------------------------------------------
 template <int HD>
 __global__ void __launch_bounds__(128) attn_kq_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, float *__restrict__ kq,
-                                                      const int *__restrict__ n_past, int gqa, int n_head, int n_head_kv, int n_ctx) {
+                                                      const int *__restrict__ n_past, int gqa, int n_head, int n_head_kv, int n_ctx, unsigned long long *prof) {
     __shared__ __align__(16) __half q16[HD];
     __shared__ __align__(16) __half kt[64 * HD];
-    const int n_kv = __ldg(n_past) + 1;
+    pdl_trigger();
+    pdl_wait();
+    prof_begin(prof);
+    const int n_kv = __ldcg(n_past) + 1;
     const int j0 = blockIdx.x * 64, h = blockIdx.y;
     if (j0 >= n_kv) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,9 +199,9 @@ __global__ void __launch_bounds__(128) attn_kq_kernel(const float *__restrict__ 
 #pragma unroll
     for (int u = 0; u < NV; u++) {
         const int i = tid + u * 128, rr = i / VPR, cc = i % VPR;
-        v[u] = rr < rows ? __ldg((const int4 *)(Kl + (int64_t)(j0 + rr) * gqa + hk * HD) + cc) : make_int4(0, 0, 0, 0);
+        v[u] = rr < rows ? __ldcg((const int4 *)(Kl + (int64_t)(j0 + rr) * gqa + hk * HD) + cc) : make_int4(0, 0, 0, 0);
     }
-    for (int i = tid; i < HD; i += 128) q16[i] = __float2half_rn(q[h * HD + i]);
+    for (int i = tid; i < HD; i += 128) q16[i] = __float2half_rn(__ldcg(q + h * HD + i));
 #pragma unroll
     for (int u = 0; u < NV; u++) ((int4 *)kt)[tid + u * 128] = v[u];
     __syncthreads();
@@ -163,17 +213,21 @@ __global__ void __launch_bounds__(128) attn_kq_kernel(const float *__restrict__ 
         s = f16dot_tree(s);
         if (lane == 0) kq[(int64_t)h * n_ctx + j0 + jj] = (float)(double)s;
     }
+    prof_end(prof);
 }
 
 // ---- 4: scale + soft_max + KQV for 32 channels of one head, then quantize those 32 outputs (one block of wo's input) ---------------
 constexpr int KC = 128;
 __global__ void __launch_bounds__(128) attn_sv_kernel(const float *__restrict__ kq, const __half *__restrict__ Vl, int4 *__restrict__ xpack_out,
                                                       const int *__restrict__ n_past, const uint16_t *__restrict__ lut_exp, float kq_scale,
-                                                      int hd, int n_head, int n_head_kv, int n_ctx, int q81, int off, int scale16) {
+                                                      int hd, int n_head, int n_head_kv, int n_ctx, int q81, int off, int scale16, unsigned long long *prof) {
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ double shd[8];
     __shared__ float shf[4], stash[32];
-    const int n_kv = __ldg(n_past) + 1;
+    pdl_trigger();
+    pdl_wait();
+    prof_begin(prof);
+    const int n_kv = __ldcg(n_past) + 1;
     const int per_head = hd / 32, h = blockIdx.x / per_head, c0 = (blockIdx.x - h * per_head) * 32;
     const int hk = h / (n_head / n_head_kv);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,14 +239,14 @@ __global__ void __launch_bounds__(128) attn_sv_kernel(const float *__restrict__ 
     const int np = n_kv & ~31;
     if (np < n_kv) {
         const int rr = tid >> 2, part = tid & 3;
-        ((int4 *)vleft)[tid] = __ldg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + np) + part);
+        ((int4 *)vleft)[tid] = __ldcg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + np) + part);
     }
     int4 pre[KC / 32];
     auto fetch = [&](int k0) {
 #pragma unroll
         for (int u = 0; u < KC / 32; u++) {
             const int i = tid + u * 128, rr = i / (KC / 8), cc = i - rr * (KC / 8);
-            pre[u] = __ldg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + k0) + cc);
+            pre[u] = __ldcg((const int4 *)(Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + k0) + cc);
         }
     };
     if (np > 0) fetch(0);
@@ -201,7 +255,7 @@ __global__ void __launch_bounds__(128) attn_sv_kernel(const float *__restrict__ 
     for (int jb = 0; jb < n_kv; jb += SB * 128) {
         float sv[SB];
 #pragma unroll
-        for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; sv[u] = j < n_kv ? kq[(int64_t)h * n_ctx + j] : 0.f; }
+        for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; sv[u] = j < n_kv ? __ldcg(kq + (int64_t)h * n_ctx + j) : 0.f; }
 #pragma unroll
         for (int u = 0; u < SB; u++) { const int j = jb + tid + u * 128; if (j < n_kv) { const float v = __fmul_rn(sv[u], kq_scale); sc[j] = v; mx = fmaxf(mx, v); } }
     }
@@ -251,25 +305,180 @@ __global__ void __launch_bounds__(128) attn_sv_kernel(const float *__restrict__ 
     }
     __syncthreads();
     if (warp == 0) pack_quad(((const float4 *)stash)[lane & 7], xpack_out + (int64_t)((h * hd + c0) / QK) * 4, lane, lane < 8, q81, off, scale16);
+    prof_end(prof);
+}
+
+// ---- 3+4 fused: KQ, scale, soft_max, KQV and the quantize epilogue for one head, as ONE cluster of hd/32 CTAs ----------------------------
+// CTA `part` of the cluster owns 32 channels of the head (its V rows are staged by cp.async at kernel entry, long before they are needed)
+// and 1/(hd/32) of the cached positions for KQ; the scaled scores are written straight into every CTA's shared memory (DSMEM) and one
+// cluster barrier later each CTA runs the soft_max on the full row and its own 32 KQV dots.  No global round trip between the phases.
+//
+// ggml_vec_dot_f16 (LC/ggml.c:1573-1610) keeps 32 f32 chains, chain l over elements k = l (mod 32); here thread u (0..3) of a quad owns
+// chains 8u..8u+7 of one dot, so every load is a 16-byte vector, and the reduction tree (offsets 16, 8, 4, 1, 2) is two quad shuffles plus
+// in-thread adds in exactly that association.
+__device__ __forceinline__ float quad_tree(float (&acc)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = __fadd_rn(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));     // chain l += chain l + 16
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = __fadd_rn(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 1));     // l += l + 8   (valid in u == 0)
+    const float r0 = __fadd_rn(acc[0], acc[4]), r1 = __fadd_rn(acc[1], acc[5]), r2 = __fadd_rn(acc[2], acc[6]), r3 = __fadd_rn(acc[3], acc[7]);   // l += l + 4
+    return __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));                                                // down 1, down 2
+}
+__device__ __forceinline__ void fma8(float (&acc)[8], const int4 &a, const int4 &b) {
+    const __half2 *ah = (const __half2 *)&a, *bh = (const __half2 *)&b;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float2 af = __half22float2(ah[e]), bf = __half22float2(bh[e]);
+        acc[2 * e] = __fmaf_rn(af.x, bf.x, acc[2 * e]); acc[2 * e + 1] = __fmaf_rn(af.y, bf.y, acc[2 * e + 1]);
+    }
+}
+
+constexpr int ATH = 256;
+__global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, const __half *__restrict__ Vl,
+                                                         int4 *__restrict__ xpack_out, const int *__restrict__ n_past, const uint16_t *__restrict__ lut_exp,
+                                                         float kq_scale, int hd, int n_head, int n_head_kv, int gqa, int n_ctx, int q81, int off, int scale16,
+                                                         unsigned long long *prof) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) uint8_t sm[];
+    __shared__ double shd[ATH / 32];
+    __shared__ float shf[ATH / 32], stash[32];
+    prof_begin(prof);
+    const int per_head = hd / 32, h = blockIdx.x / per_head, part = blockIdx.x - h * per_head, c0 = part * 32;
+    const int hk = h / (n_head / n_head_kv);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, u = tid & 3;
+    const int vstride = n_ctx + 32;                             // halves; (n_ctx + 32) * 2 B = 64 B mod 128 B: the two columns of a quarter-warp hit different banks
+    float *sc = (float *)sm;
+    __half *p16 = (__half *)(sm + (size_t)n_ctx * 4);
+    __half *q16 = p16 + n_ctx;
+    __half *vs = (__half *)(sm + (((size_t)n_ctx * 6 + (size_t)hd * 2 + 127) & ~(size_t)127));
+    float qv = 0.f;
+    if (tid < hd) qv = __ldcg(q + h * hd + tid);               // in flight together with the n_past load (hd <= 256 = ATH)
+    const int n_kv = __ldcg(n_past) + 1;
+    const int np = n_kv & ~31;
+
+    {   // V rows of this CTA's 32 channels: all copies in flight now, consumed after the soft_max
+        const int cpr = (n_kv + 7) / 8;                          // 16-byte chunks per row
+        for (int i = tid; i < 32 * cpr; i += ATH) {
+            const int rr = i / cpr, cc = i - rr * cpr;
+            cp16(smem_u32(vs + rr * vstride + cc * 8), Vl + (int64_t)(hk * hd + c0 + rr) * n_ctx + cc * 8);
+        }
+    }
+    if (tid < hd) q16[tid] = __float2half_rn(qv);
+    cluster.sync();                                             // q16 visible; every CTA of the cluster is running (its shared memory may be written)
+
+    // ---- KQ for this CTA's share of the positions ----
+    {
+        const int per = (n_kv + per_head - 1) / per_head, j0 = part * per, j1 = n_kv < j0 + per ? n_kv : j0 + per;
+        const int nvec = hd / 32;                                // 16-byte loads per thread per position (chunks i = 0..nvec-1)
+        constexpr int PU = 4;                                    // positions per quad per pass: up to 4 * nvec 16-byte loads in flight per thread
+        for (int jb = j0; jb < j1; jb += PU * (ATH / 4)) {
+            int4 kv[PU][4];
+#pragma unroll
+            for (int pu = 0; pu < PU; pu++) {
+                const int j = jb + pu * (ATH / 4) + (tid >> 2);
+                const __half *krow = Kl + (int64_t)(j < j1 ? j : j0) * gqa + hk * hd + 8 * u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (i < nvec) kv[pu][i] = j < j1 ? __ldcg((const int4 *)(krow + 32 * i)) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int pu = 0; pu < PU; pu++) {
+                const int j = jb + pu * (ATH / 4) + (tid >> 2);
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[e] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (i < nvec) fma8(acc, kv[pu][i], *(const int4 *)(q16 + 32 * i + 8 * u));
+                const float s = quad_tree(acc);
+                if (j < j1 && u < per_head) cluster.map_shared_rank(sc, u)[j] = __fmul_rn(s, kq_scale);   // thread u of the quad feeds CTA u
+            }
+        }
+    }
+    cluster.sync();
+
+    // ---- soft_max over sc[0, n_kv) (ggml_compute_forward_soft_max_f32, LC/ggml.c:11700-11770: fp16 exp table, double row sum) ----
+    float mx = -INFINITY;
+    for (int j = tid; j < n_kv; j += ATH) mx = fmaxf(mx, sc[j]);
+    mx = warp_max(mx);
+    if (lane == 0) shf[warp] = mx;
+    __syncthreads();
+    mx = shf[0];
+#pragma unroll
+    for (int i = 1; i < ATH / 32; i++) mx = fmaxf(mx, shf[i]);
+    double s = 0.0;
+    constexpr int SB = 4;                                        // table look-ups in flight per thread
+    for (int jb = 0; jb < n_kv; jb += SB * ATH) {
+        uint16_t ev16[SB];
+#pragma unroll
+        for (int k = 0; k < SB; k++) { const int j = jb + tid + k * ATH; ev16[k] = j < n_kv ? __ldg(lut_exp + f32_to_f16_bits(__fsub_rn(sc[j], mx))) : (uint16_t)0; }
+#pragma unroll
+        for (int k = 0; k < SB; k++) { const int j = jb + tid + k * ATH; if (j < n_kv) { const float ev = f16_bits_to_f32(ev16[k]); sc[j] = ev; s += (double)ev; } }
+    }
+    s = warp_sum(s);
+    if (lane == 0) shd[warp] = s;
+    __syncthreads();
+    const float inv = (float)(1.0 / (((shd[0] + shd[1]) + (shd[2] + shd[3])) + ((shd[4] + shd[5]) + (shd[6] + shd[7]))));
+    for (int j = tid; j < n_kv; j += ATH) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    // ---- KQV: 32 channels x 4 threads ----
+    if (tid < 128) {
+        const int col = tid >> 2;
+        const __half *vrow = vs + col * vstride;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[e] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < np; k += 32) fma8(acc, *(const int4 *)(vrow + k + 8 * u), *(const int4 *)(p16 + k + 8 * u));
+        const float a = quad_tree(acc);
+        if (u == 0) {
+            double sumf = (double)a;
+            for (int k = np; k < n_kv; k++) sumf += (double)__fmul_rn(__half2float(vrow[k]), __half2float(p16[k]));
+            stash[col] = (float)sumf;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) pack_quad(((const float4 *)stash)[lane & 7], xpack_out + (int64_t)((h * hd + c0) / QK) * 4, lane, lane < 8, q81, off, scale16);
+    prof_end(prof);
 }
 
 template <int TYPE, int EPI>
-void launch_mmv(const QWeight &w, const MmvArgs &A, cudaStream_t st) {
+void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
+    constexpr int ROWS = SR, CB = SCB;
     using T = St<TYPE>;
-    const int smem = 256 + T::RING_BYTES + (int)w.nb * 64 + 256;
-    static int smem_set = 0, ctas_per_sm = 0, sms = 0, occ_smem = -1;
-    if (smem > smem_set) {
-        B200_ASSERT(smem <= 227 * 1024);
-        B200_CHECK(cudaFuncSetAttribute(mmv_fused_kernel<TYPE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-    }
+    static int smem_set = 0, sms = 0, depth_cap = -1;
+    static std::map<int, std::array<int, SST_MAX + 1>> occ_by_nb;
     if (!sms) { int dev; B200_CHECK(cudaGetDevice(&dev)); B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
-    if (occ_smem != smem) { B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, mmv_fused_kernel<TYPE, EPI>, STHREADS, smem)); occ_smem = smem; }
+    if (depth_cap < 0) { const char *e = getenv("B200_RING_DEPTH"); depth_cap = e ? atoi(e) : SST_MAX; if (depth_cap < 2) depth_cap = 2; if (depth_cap > SST_MAX) depth_cap = SST_MAX; }
+    auto smem_of = [&](int nst) { return 256 + T::ring_bytes(nst) + (int)w.nb * 64 + 256; };
+    if (smem_of(SST_MAX) > smem_set) {
+        const int want = smem_of(SST_MAX) < 227 * 1024 ? smem_of(SST_MAX) : 227 * 1024;
+        B200_CHECK(cudaFuncSetAttribute(mmv_fused_kernel<TYPE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        smem_set = smem_of(SST_MAX);
+    }
+    auto it = occ_by_nb.find((int)w.nb);
+    if (it == occ_by_nb.end()) {                                          // CTAs per SM for every ring depth at this activation length
+        std::array<int, SST_MAX + 1> o{};
+        for (int nst = 2; nst <= SST_MAX; nst++)
+            if (smem_of(nst) <= 227 * 1024) B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[nst], mmv_fused_kernel<TYPE, EPI>, STHREADS, smem_of(nst)));
+        it = occ_by_nb.emplace((int)w.nb, o).first;
+    }
+    const std::array<int, SST_MAX + 1> &occ = it->second;
     constexpr int G = EPI == EPI_SILU ? 2 : 1;
-    const int64_t groups = ((w.N + SR - 1) / SR + G - 1) / G;
-    const int64_t slots = (int64_t)sms * (ctas_per_sm > 0 ? ctas_per_sm : 1);
-    mmv_fused_kernel<TYPE, EPI><<<(unsigned)(groups < slots ? groups : slots), STHREADS, smem, st>>>(w, A);
-    B200_CHECK(cudaGetLastError());
+    const int64_t groups = ((w.N + ROWS - 1) / ROWS + G - 1) / G;
+    // Ring depth: the deepest ring that still keeps every row group resident at once (more bytes in flight per CTA: the small matrices
+    // -- 128 groups for 148 SMs -- are bound by HBM round trips per CTA, not by bandwidth); never deeper than one group's chunk count.
+    const int chunks = (int)((w.nb + CB - 1) / CB) * G;
+    const int base = SST < depth_cap ? SST : depth_cap;
+    int nst = base;
+    B200_ASSERT(occ[nst] > 0);
+    const int64_t need = groups < (int64_t)sms * occ[base] ? groups : (int64_t)sms * occ[base];
+    for (int c = base + 1; c <= depth_cap && c <= chunks; c++)
+        if (occ[c] > 0 && (int64_t)sms * occ[c] >= need) nst = c;
+    A.nst = nst;
+    const int64_t slots = (int64_t)sms * occ[nst];
+    launch_k<1>(mmv_fused_kernel<TYPE, EPI>, dim3((unsigned)(groups < slots ? groups : slots)), dim3(STHREADS), (size_t)smem_of(nst), st, w, A);
 }
 
 template <int TYPE>
@@ -277,32 +486,51 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     const int q81 = has_min(TYPE) ? 1 : 0, off = TYPE == T_Q5_0 ? 16 : 0, s16 = TYPE == T_Q4_0 ? 1 : 0;
     const int e = P.e, f = P.f;
     int n = 0;
+    auto pr = [&]() -> unsigned long long * { return P.prof && n < B200_PROF_SLOTS ? P.prof + n : nullptr; };   // timeline slot of the next launch
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
+    // attention: one cluster launch per layer (default) or the two-kernel variant (B200_ATTN_FUSED=0, or head sizes a cluster cannot cover)
+    static const bool fused_env = !(getenv("B200_ATTN_FUSED") && getenv("B200_ATTN_FUSED")[0] == '0');
+    const size_t fa_smem = (((size_t)P.n_ctx * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (P.n_ctx + 32) * 2;
+    const bool fused_attn = fused_env && P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 32 == 0 && fa_smem <= 227 * 1024;
+    static size_t fa_set = 48 * 1024;
+    if (fused_attn && fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
     const size_t sv_smem = (size_t)P.n_ctx * 6 + 32 * KC * 2 + 32 * 32 * 2;
     static size_t sv_set = 48 * 1024;
     if (sv_smem > sv_set) { B200_CHECK(cudaFuncSetAttribute(attn_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem)); sv_set = sv_smem; }
     for (int il = 0; il < P.n_layer; il++) {
         const DecodeLayer &L = layers[il];
-        norm_pack_kernel<<<(e / QK + 31) / 32, 256, 0, st>>>(P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16); n++;
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr()); n++;
         MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
-        launch_mmv<TYPE, EPI_QKV>(L.wqkv, A, st); n++;
-        if (P.hd == 128) attn_kq_kernel<128><<<dim3((n_kv_bucket + 63) / 64, P.n_head), 128, 0, st>>>(P.q, L.K, P.kq, P.n_past, P.gqa, P.n_head, P.n_head_kv, P.n_ctx);
-        else             attn_kq_kernel<64><<<dim3((n_kv_bucket + 63) / 64, P.n_head), 128, 0, st>>>(P.q, L.K, P.kq, P.n_past, P.gqa, P.n_head, P.n_head_kv, P.n_ctx);
-        n++;
-        attn_sv_kernel<<<P.n_head * (P.hd / 32), 128, sv_smem, st>>>(P.kq, L.V, P.xpack_d, P.n_past, P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.n_ctx,
-                                                                      q81, off, s16); n++;
+        A.prof = pr(); launch_mmv<TYPE, EPI_QKV>(L.wqkv, A, st); n++;
+        if (fused_attn) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(P.n_head * (P.hd / 32)); cfg.blockDim = dim3(ATH); cfg.dynamicSmemBytes = fa_smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = P.hd / 32; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
+                                          (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, q81, off, s16, pr()));
+            n++;
+        } else {
+            launch_k(P.hd == 128 ? attn_kq_kernel<128> : attn_kq_kernel<64>, dim3((n_kv_bucket + 63) / 64, P.n_head), dim3(128), 0, st,
+                     P.q, L.K, P.kq, P.n_past, P.gqa, P.n_head, P.n_head_kv, P.n_ctx, pr());
+            n++;
+            launch_k(attn_sv_kernel, dim3(P.n_head * (P.hd / 32)), dim3(128), sv_smem, st, P.kq, L.V, P.xpack_d, P.n_past, P.lut_exp, P.kq_scale, P.hd, P.n_head,
+                     P.n_head_kv, P.n_ctx, q81, off, s16, pr()); n++;
+        }
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;
-        launch_mmv<TYPE, EPI_RES>(L.wo, Bo, st); n++;
-        norm_pack_kernel<<<(e / QK + 31) / 32, 256, 0, st>>>(P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16); n++;
+        Bo.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.wo, Bo, st); n++;
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr()); n++;
         MmvArgs C{}; C.xpack = xpack_a; C.xpack_out = P.xpack_f; C.lut_silu = P.lut_silu; C.q81 = q81; C.off = off; C.scale16 = s16;
-        launch_mmv<TYPE, EPI_SILU>(L.w13, C, st); n++;
+        C.prof = pr(); launch_mmv<TYPE, EPI_SILU>(L.w13, C, st); n++;
         MmvArgs D{}; D.xpack = P.xpack_f; D.dst = P.x; D.addend = P.ff;
-        launch_mmv<TYPE, EPI_RES>(L.w2, D, st); n++;
+        D.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.w2, D, st); n++;
     }
-    norm_pack_kernel<<<(e / QK + 31) / 32, 256, 0, st>>>(P.x, P.norm, xpack_a, e, P.eps, q81, off, s16); n++;
+    launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr()); n++;
     MmvArgs Z{}; Z.xpack = xpack_a; Z.dst = P.logits; Z.addend = nullptr; Z.n_past_inc = P.n_past;
-    launch_mmv<TYPE, EPI_LOGITS>(P.output, Z, st); n++;
+    Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS>(P.output, Z, st); n++;
     B200_CHECK(cudaGetLastError());
     (void)f;
     if (launches) *launches = n;

@@ -11,8 +11,16 @@
 // The tensor core replaces 8 dp4a + 8 int->float conversions per (token, row, block); what remains on the CUDA cores is the part that
 // defines the reference's rounding: one f32 product d_w*d_x and eight ordered fmas.  Results are bit-identical to exact.cu (tests).
 //
-// CTA = 8 warps = 128 tokens x 16 weight rows; warp w owns rows (2w, 2w+1) for all 8 token tiles (64 accumulator registers).
-// K loop: double-buffered cp.async pipeline over 4-block stages (activations as f16 [token][k], weights in the planes layout).
+// CTA = 8 warps = 64 tokens x 32 weight rows (L2 bytes per unit of work ~ 72/rows + 18/tokens); warp tile = 32 tokens x 8 rows
+// (2 token tiles x 4 row pairs, 64 accumulator registers).  K loop: 3-stage cp.async pipeline over 4-block stages.
+//
+// k ORDER inside a 16-element chunk.  The k index is a dummy, so the chunk's elements are assigned to MMA k slots such that lane L' (elements
+// 4L'..4L'+3) occupies k = {2L', 2L'+1, 2L'+8, 2L'+9}: exactly the four k slots ONE thread (t = L') holds in both the A and the B fragment.
+//   A: thread (g, t) needs elements 4t..4t+3 of a chunk for tokens g and g+8: quantize_act_f16 writes xh directly in that fragment order
+//      ([16-token tile][block][chunk][thread] x 16 B), so one conflict-free 16-byte shared load IS the {a0..a3} register quad (no ldmatrix, no moves);
+//   B: column g = (row g >> 2 of the pair, lane g & 3) is non-zero only in thread t == (g & 3): one predicated 16-byte load per (row pair, block)
+//      of fragments that the CTA expands ONCE per stage (nibbles -> f16) into `sB`; the other 24 threads keep registers that stay zero.
+// Per warp and block: 16 HMMA + 64 FFMA + 16 FMUL (the reference's arithmetic) + 16 shared loads.
 #include <string.h>
 
 #include "kernels.cuh"
@@ -21,41 +29,43 @@ namespace b200 {
 
 namespace {
 
-constexpr int XM = 128, XN = 16, XKB = 4, XST = 2, XTH = 256;   // 2 stages of 41 KB: two CTAs (16 warps) per SM
-constexpr int XA_STRIDE = XKB * 64 + 16;          // bytes per token row of f16 activations in smem (+16: conflict-free ldmatrix)
+constexpr int XM = 64, XN = 32, XKB = 4, XST = 3, XTH = 256;    // 3 stages of ~25 KB + 9 KB of expanded operands, two CTAs (16 warps) per SM
+constexpr int XTG = XM / 32;                                     // warps along the token axis (the other XTH/32/XTG split the rows, 8 each)
+static_assert((XTH / 32 / XTG) * 8 == XN, "warp grid must cover the CTA tile");
 constexpr int XS_STRIDE = XKB * 8 + 8;            // float2 {d, s} per block
+constexpr int XB_BYTES = (XN / 2) * XKB * 8 * 16; // expanded B fragments of one stage: [row pair][block][column g] x 16 B
+constexpr int XW_BYTES = XN * XKB * 8;            // {d, m} as f32 per (row, block)
 
 template <int TYPE> struct Xm {
     static constexpr int QS = (TYPE == T_Q8_0) ? 32 : 16;
     static constexpr int DM = (TYPE == T_Q4_1 || TYPE == T_Q5_1) ? 4 : 2;
     static constexpr bool QH = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
     static constexpr bool MIN = (TYPE == T_Q4_1 || TYPE == T_Q5_1);
-    static constexpr int A_BYTES = XM * XA_STRIDE, S_BYTES = XM * XS_STRIDE;
-    static constexpr int Q_BYTES = XN * XKB * QS, D_BYTES = XN * XKB * DM, H_BYTES = XN * XKB * 4;
-    static constexpr int STAGE = A_BYTES + S_BYTES + Q_BYTES + ((D_BYTES + 15) & ~15) + H_BYTES;
+    static constexpr int A_BYTES = (XM / 16) * XKB * 1024, S_BYTES = XM * XS_STRIDE;
+    static constexpr int Q_BYTES = XN * XKB * QS, D_BYTES = (XN * XKB * DM + 15) & ~15, H_BYTES = QH ? XN * XKB * 4 : 0;
+    static constexpr int STAGE = A_BYTES + S_BYTES + Q_BYTES + D_BYTES + H_BYTES;
+    static constexpr int SMEM = XST * STAGE + XB_BYTES + XW_BYTES;
+    // fp16 magic: 0x6400 | n == 1024 + n; subtracting 1024 + bias leaves the signed integer weight exactly
+    static constexpr uint32_t OFF = TYPE == T_Q4_0 ? 0x64086408u : TYPE == T_Q5_0 ? 0x64106410u : TYPE == T_Q8_0 ? 0x64806480u : 0x64006400u;
 };
 
-__device__ __forceinline__ void cpa16(void *smem, const void *g, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g), "r"(src_bytes));
+__device__ __forceinline__ void cpa16(uint32_t smem, const void *g, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(g), "r"(src_bytes));
 }
-__device__ __forceinline__ void cpa8(void *smem, const void *g, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g), "r"(src_bytes));
+__device__ __forceinline__ void cpa8(uint32_t smem, const void *g, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem), "l"(g), "r"(src_bytes));
 }
-__device__ __forceinline__ void cpa4(void *smem, const void *g, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g), "r"(src_bytes));
+__device__ __forceinline__ void cpa4(uint32_t smem, const void *g, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem), "l"(g), "r"(src_bytes));
 }
-__device__ __forceinline__ void ldm_x4(uint32_t (&r)[4], const void *smem) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"((uint32_t)__cvta_generic_to_shared(smem)));
-}
-__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
                  : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.0f));
 }
-// two small integers (each in one byte of `v`: byte 0 and byte 1) -> half2, minus `off`: exact (0x6400 | n == 1024 + n in fp16)
-__device__ __forceinline__ uint32_t ints_to_half2(uint32_t v, uint32_t mask, uint32_t off_h2) {
-    uint32_t p = (__byte_perm(v, 0, 0x4140) & mask) | 0x64006400u;        // [n0, 0x64, n1, 0x64] = half2(1024 + n0, 1024 + n1)
+// bytes (lo, hi) of `v` -> half2(1024 + lo, 1024 + hi) - off   (exact)
+__device__ __forceinline__ uint32_t bytes_to_half2(uint32_t v, uint32_t sel, uint32_t off_h2) {
+    const uint32_t p = __byte_perm(v, 0x64646464u, sel);
     __half2 a, o;
     memcpy(&a, &p, 4); memcpy(&o, &off_h2, 4);
     const __half2 h = __hsub2(a, o);
@@ -69,135 +79,164 @@ __global__ void __launch_bounds__(XTH, 2) mm_exact_mma_kernel(const QWeight w, c
                                                               const float *__restrict__ addend, int64_t lda) {
     using T = Xm<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *const sB = smem + XST * T::STAGE, *const sW = sB + XB_BYTES;
+    const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int64_t m_base = (int64_t)blockIdx.y * XM, n_base = (int64_t)blockIdx.x * XN;
     const int nb = (int)w.nb, ktiles = (nb + XKB - 1) / XKB;
-    const int64_t K = (int64_t)nb * QK;
 
-    auto stage = [&](int s) { return smem + (size_t)s * T::STAGE; };
+    // ---- per-thread copy plan: byte offsets of this thread's rows inside each plane (32-bit: planes are < 4 GB), fixed for the whole K loop ----
+    auto clamp_m = [&](int r) { const int64_t m = m_base + r; return m < B ? m : B - 1; };
+    auto clamp_n = [&](int r) { const int64_t n = n_base + r; return n < w.N ? n : w.N - 1; };
+    uint32_t a_off[XM / 16];                                            // activations: token tile i of the CTA = 256 x 16 B per block-stage, contiguous in xh
+    const int64_t n_tiles = (B + 15) / 16;
+#pragma unroll
+    for (int i = 0; i < XM / 16; i++) {
+        const int64_t tile = m_base / 16 + i < n_tiles ? m_base / 16 + i : n_tiles - 1;
+        a_off[i] = (uint32_t)(tile * nb * 1024 + tid * 16);
+    }
+    const uint32_t s_off = (uint32_t)((clamp_m(tid >> 2) * nb + (tid & 3)) * 8);          // {d, s}: thread -> (token tid/4, block tid%4)
+    constexpr int QC = T::QS / 16;                                      // 16-byte copies per weight block
+    const uint32_t q_off = (uint32_t)(clamp_n(tid / (XKB * QC)) * nb * T::QS + (tid % (XKB * QC)) * 16);
+    constexpr int DC = XKB * T::DM / 4;                                 // 4-byte copies per weight row per stage
+    const uint32_t d_off = (uint32_t)(clamp_n(tid / DC) * nb * T::DM + (tid % DC) * 4);
+    const uint32_t h_off = (uint32_t)((clamp_n(tid >> 2) * nb + (tid & 3)) * 4);
+
     auto load_stage = [&](int s, int kt) {
-        uint8_t *sA = stage(s), *sS = sA + T::A_BYTES, *sQ = sS + T::S_BYTES, *sD = sQ + T::Q_BYTES, *sH = sD + ((T::D_BYTES + 15) & ~15);
+        const uint32_t sA = smem_u + s * T::STAGE, sS = sA + T::A_BYTES, sQ = sS + T::S_BYTES, sD = sQ + T::Q_BYTES, sH = sD + T::D_BYTES;
         const int b0 = kt * XKB;
-        for (int c = tid; c < XM * XKB * 4; c += XTH) {                  // activations: 4 x 16 B per (token, block)
-            const int r = c / (XKB * 4), cc = c % (XKB * 4), b = b0 + cc / 4;
-            const int64_t m = m_base + r < B ? m_base + r : B - 1;
-            const bool ok = b < nb;
-            cpa16(sA + r * XA_STRIDE + cc * 16, xh + m * K + (int64_t)(ok ? b : 0) * QK + (cc & 3) * 8, ok ? 16 : 0);
+        {
+            const int ok = b0 + (tid >> 6) < nb ? 16 : 0;                                  // 64 copies per block
+            const uint8_t *src = (const uint8_t *)xh + (size_t)b0 * 1024;
+#pragma unroll
+            for (int i = 0; i < XM / 16; i++) cpa16(sA + i * (XKB * 1024) + tid * 16, src + (ok ? a_off[i] : 0u), ok);
         }
-        for (int c = tid; c < XM * XKB; c += XTH) {                      // {d, s} per (token, block)
-            const int r = c / XKB, b = b0 + c % XKB;
-            const int64_t m = m_base + r < B ? m_base + r : B - 1;
-            const bool ok = b < nb;
-            cpa8(sS + r * XS_STRIDE + (c % XKB) * 8, xds + m * nb + (ok ? b : 0), ok ? 8 : 0);
+        if (tid < XM * XKB) cpa8(sS + (tid >> 2) * XS_STRIDE + (tid & 3) * 8, (const uint8_t *)xds + (size_t)b0 * 8 + (b0 + (tid & 3) < nb ? s_off : 0u), b0 + (tid & 3) < nb ? 8 : 0);
+        if (tid < XN * XKB * QC) {
+            const int ok = b0 + (tid % (XKB * QC)) / QC < nb ? 16 : 0;
+            cpa16(sQ + tid * 16, w.qs + (size_t)b0 * T::QS + (ok ? q_off : 0u), ok);
         }
-        for (int c = tid; c < XN * XKB * (T::QS / 16); c += XTH) {       // weight quants
-            const int r = c / (XKB * (T::QS / 16)), cc = c % (XKB * (T::QS / 16)), b = b0 + cc / (T::QS / 16);
-            const int64_t n = n_base + r < w.N ? n_base + r : w.N - 1;
-            const bool ok = b < nb;
-            cpa16(sQ + (r * XKB * T::QS) + cc * 16, w.qs + (n * nb + (ok ? b : 0)) * T::QS + (cc % (T::QS / 16)) * 16, ok ? 16 : 0);
+        if (tid < XN * DC) {
+            const int ok = b0 + (tid % DC) * (4 / T::DM) < nb ? 4 : 0;                    // nb is even: a 4-byte copy of two fp16 scales is all-or-nothing
+            cpa4(sD + tid * 4, (const uint8_t *)w.dm + (size_t)b0 * T::DM + (ok ? d_off : 0u), ok);
         }
-        for (int c = tid; c < XN * XKB * T::DM / 4; c += XTH) {          // weight scales (4-byte copies: 2 blocks of fp16 d, or one {d, m})
-            const int per_row = XKB * T::DM / 4, r = c / per_row, cc = c % per_row, b = b0 + cc * (4 / T::DM);
-            const int64_t n = n_base + r < w.N ? n_base + r : w.N - 1;
-            const bool ok = b < nb;                                       // nb is even
-            cpa4(sD + r * XKB * T::DM + cc * 4, (const uint8_t *)w.dm + (n * nb + (ok ? b : 0)) * T::DM, ok ? 4 : 0);
+        if (T::QH && tid < XN * XKB) {
+            const int ok = b0 + (tid & 3) < nb ? 4 : 0;
+            cpa4(sH + tid * 4, (const uint8_t *)w.qh + (size_t)b0 * 4 + (ok ? h_off : 0u), ok);
         }
-        if (T::QH)
-            for (int c = tid; c < XN * XKB; c += XTH) {
-                const int r = c / XKB, b = b0 + c % XKB;
-                const int64_t n = n_base + r < w.N ? n_base + r : w.N - 1;
-                const bool ok = b < nb;
-                cpa4(sH + (r * XKB + c % XKB) * 4, w.qh + n * nb + (ok ? b : 0), ok ? 4 : 0);
-            }
     };
 
-    // this thread's role in the B operand: column g = lane (g & 3) of row (g < 4 ? pair row 0 : pair row 1)
-    const int cg = g & 3;
-    const bool b_nonzero = (t >> 1) == (cg & 1);
-    const bool b_second = (cg >> 1) != 0;                  // value sits in b1 (k 8..15 of the chunk) instead of b0
-    const int kbyte = 2 * t + 8 * (cg >> 1);               // first of the two element indices inside the 16-element chunk
-    const int brow = warp * 2 + (g >> 2);                  // weight row (in the CTA tile) feeding this thread's B column
-    const int crow = warp * 2 + (t >> 1);                  // weight row of this thread's two C columns
+    // ---- once per stage: nibbles -> f16 B fragments (sB) and fp16 scales -> f32 (sW) ----
+    auto expand_stage = [&](int s) {
+        const uint8_t *sQ = smem + s * T::STAGE + T::A_BYTES + T::S_BYTES, *sD = sQ + T::Q_BYTES, *sH = sD + T::D_BYTES;
+#pragma unroll
+        for (int it = 0; it < XN * XKB * 4 / XTH; it++) {
+            const int i = tid + it * XTH, cg = i & 3, b = (i >> 2) & (XKB - 1), r = i >> 4;      // (row r, block b, lane pair cg / cg + 4)
+            uint32_t lo, hi;                                                                       // 4 weights of chunk 0 / chunk 1, one per byte
+            if (TYPE == T_Q8_0) {
+                lo = *(const uint32_t *)(sQ + (r * XKB + b) * 32 + 4 * cg) ^ 0x80808080u;         // int8 -> biased 0..255
+                hi = *(const uint32_t *)(sQ + (r * XKB + b) * 32 + 16 + 4 * cg) ^ 0x80808080u;
+            } else {
+                const uint32_t v = *(const uint32_t *)(sQ + (r * XKB + b) * 16 + 4 * cg);
+                lo = v & 0x0F0F0F0Fu; hi = (v >> 4) & 0x0F0F0F0Fu;
+                if (T::QH) {
+                    const uint32_t qh = *(const uint32_t *)(sH + (r * XKB + b) * 4);
+                    lo |= ((((qh >> (4 * cg)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;          // bit j -> bit 4 of byte j
+                    hi |= ((((qh >> (16 + 4 * cg)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
+                }
+            }
+            uint4 f;
+            f.x = bytes_to_half2(lo, 0x4140u, T::OFF); f.y = bytes_to_half2(lo, 0x4342u, T::OFF);
+            f.z = bytes_to_half2(hi, 0x4140u, T::OFF); f.w = bytes_to_half2(hi, 0x4342u, T::OFF);
+            *(uint4 *)(sB + ((((r >> 1) * XKB + b) * 8) + (r & 1) * 4 + cg) * 16) = f;
+        }
+        if (tid < XN * XKB) {
+            float2 dm;
+            if (T::MIN) { const __half2 h = *(const __half2 *)(sD + tid * 4); dm = make_float2(__low2float(h), __high2float(h)); }
+            else dm = make_float2(__half2float(*(const __half *)(sD + tid * 2)), 0.f);
+            *(float2 *)(sW + tid * 8) = dm;
+        }
+    };
 
-    float acc[8][8];                                        // [token tile][chunk*4 + e]
-    float summs[8][2];
+    const int tg = warp % XTG, rg = warp / XTG;
+    const bool b_active = t == (g & 3);
+
+    float acc[2][4][8];                                     // [token tile][row pair][chunk*4 + e]
+    float summs[2][4][2];
+    uint4 bf[4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { summs[i][0] = summs[i][1] = 0.f;
+    for (int p = 0; p < 4; p++) bf[p] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.f; }
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) { summs[i][p][0] = summs[i][p][1] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[i][p][j] = 0.f; }
 
 #pragma unroll
     for (int s = 0; s < XST - 1; s++) { if (s < ktiles) load_stage(s, s); asm volatile("cp.async.commit_group;"); }
 
     for (int kt = 0; kt < ktiles; kt++) {
         asm volatile("cp.async.wait_group %0;" ::"n"(XST - 2));
-        __syncthreads();
+        __syncthreads();                                    // stage kt landed for everyone; everyone is done with sB / sW / stage kt-1
         { const int nk = kt + XST - 1; if (nk < ktiles) load_stage(nk % XST, nk); asm volatile("cp.async.commit_group;"); }
-        const uint8_t *sA = stage(kt % XST), *sS = sA + T::A_BYTES, *sQ = sS + T::S_BYTES, *sD = sQ + T::Q_BYTES, *sH = sD + ((T::D_BYTES + 15) & ~15);
-#pragma unroll
+        expand_stage(kt % XST);
+        __syncthreads();
+        const uint8_t *sA = smem + (kt % XST) * T::STAGE, *sS = sA + T::A_BYTES;
+#pragma unroll 1
         for (int b = 0; b < XKB; b++) {
-            // ---- B fragments of this block: chunk 0 = elements 0-15 (low nibbles), chunk 1 = elements 16-31 (high nibbles) ----
-            uint32_t bf[2] = {0u, 0u};
-            if (b_nonzero) {
-                if (TYPE == T_Q8_0) {
-                    const uint8_t *q = sQ + (brow * XKB + b) * 32;
-                    const int a0 = (int8_t)q[kbyte], a1 = (int8_t)q[kbyte + 1], c0 = (int8_t)q[16 + kbyte], c1 = (int8_t)q[16 + kbyte + 1];
-                    const __half2 h0 = __halves2half2(__int2half_rn(a0), __int2half_rn(a1)), h1 = __halves2half2(__int2half_rn(c0), __int2half_rn(c1));
-                    bf[0] = *(const uint32_t *)&h0; bf[1] = *(const uint32_t *)&h1;
-                } else {
-                    const uint32_t v = *(const uint16_t *)(sQ + (brow * XKB + b) * 16 + kbyte);      // bytes kbyte, kbyte+1
-                    uint32_t lo = v & 0x0F0Fu, hi = (v >> 4) & 0x0F0Fu;
-                    if (T::QH) {
-                        const uint32_t qh = *(const uint32_t *)(sH + (brow * XKB + b) * 4);
-                        lo |= (((qh >> kbyte) & 1u) << 4) | (((qh >> (kbyte + 1)) & 1u) << 12);
-                        hi |= (((qh >> (16 + kbyte)) & 1u) << 4) | (((qh >> (17 + kbyte)) & 1u) << 12);
-                    }
-                    const uint32_t off = TYPE == T_Q4_0 ? 0x64086408u : (TYPE == T_Q5_0 ? 0x64106410u : 0x64006400u);   // 1024 + {8, 16, 0}
-                    bf[0] = ints_to_half2(lo, 0x00FF00FFu, off);
-                    bf[1] = ints_to_half2(hi, 0x00FF00FFu, off);
-                }
-            }
-            float dw, mw = 0.f;
-            if (T::MIN) { const __half2 dm = *(const __half2 *)(sD + (crow * XKB + b) * 4); dw = __low2float(dm); mw = __high2float(dm); }
-            else dw = __half2float(*(const __half *)(sD + (crow * XKB + b) * 2));
+            float dw[4], mw[4];
 #pragma unroll
-            for (int mt = 0; mt < 8; mt++) {
-                const int rm = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                uint32_t a0[4], a1[4];
-                ldm_x4(a0, sA + rm * XA_STRIDE + b * 64 + (lane >> 4) * 16);            // elements 0-15
-                ldm_x4(a1, sA + rm * XA_STRIDE + b * 64 + 32 + (lane >> 4) * 16);       // elements 16-31
-                float c0[4], c1[4];
-                mma_f16(c0, a0, b_second ? 0u : bf[0], b_second ? bf[0] : 0u);
-                mma_f16(c1, a1, b_second ? 0u : bf[1], b_second ? bf[1] : 0u);
-                const float2 x0 = *(const float2 *)(sS + (mt * 16 + g) * XS_STRIDE + b * 8);
-                const float2 x1 = *(const float2 *)(sS + (mt * 16 + g + 8) * XS_STRIDE + b * 8);
-                const float d0 = __fmul_rn(dw, x0.x), d1 = __fmul_rn(dw, x1.x);
-                acc[mt][0] = __fmaf_rn(d0, c0[0], acc[mt][0]); acc[mt][1] = __fmaf_rn(d0, c0[1], acc[mt][1]);
-                acc[mt][2] = __fmaf_rn(d1, c0[2], acc[mt][2]); acc[mt][3] = __fmaf_rn(d1, c0[3], acc[mt][3]);
-                acc[mt][4] = __fmaf_rn(d0, c1[0], acc[mt][4]); acc[mt][5] = __fmaf_rn(d0, c1[1], acc[mt][5]);
-                acc[mt][6] = __fmaf_rn(d1, c1[2], acc[mt][6]); acc[mt][7] = __fmaf_rn(d1, c1[3], acc[mt][7]);
-                if (T::MIN) { summs[mt][0] = __fmaf_rn(mw, x0.y, summs[mt][0]); summs[mt][1] = __fmaf_rn(mw, x1.y, summs[mt][1]); }
+            for (int p = 0; p < 4; p++) {
+                const float2 dm = *(const float2 *)(sW + ((rg * 8 + p * 2 + (t >> 1)) * XKB + b) * 8);   // weight row of this thread's two C columns
+                dw[p] = dm.x; mw[p] = dm.y;
+                if (b_active) bf[p] = *(const uint4 *)(sB + (((rg * 4 + p) * XKB + b) * 8 + g) * 16);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                const int tok0 = tg * 32 + mt * 16;
+                const uint8_t *at = sA + ((tg * 2 + mt) * XKB + b) * 1024 + lane * 16;
+                const uint4 xa = *(const uint4 *)at;                // chunk 0: the A fragment {a0, a1, a2, a3} as stored by quantize_act_f16
+                const uint4 xb = *(const uint4 *)(at + 512);        // chunk 1
+                const float2 x0 = *(const float2 *)(sS + (tok0 + g) * XS_STRIDE + b * 8);
+                const float2 x1 = *(const float2 *)(sS + (tok0 + g + 8) * XS_STRIDE + b * 8);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    float c0[4], c1[4];
+                    mma_f16(c0, xa.x, xa.y, xa.z, xa.w, bf[p].x, bf[p].y);
+                    mma_f16(c1, xb.x, xb.y, xb.z, xb.w, bf[p].z, bf[p].w);
+                    const float d0 = __fmul_rn(dw[p], x0.x), d1 = __fmul_rn(dw[p], x1.x);
+                    float *a = acc[mt][p];
+                    a[0] = __fmaf_rn(d0, c0[0], a[0]); a[1] = __fmaf_rn(d0, c0[1], a[1]);
+                    a[2] = __fmaf_rn(d1, c0[2], a[2]); a[3] = __fmaf_rn(d1, c0[3], a[3]);
+                    a[4] = __fmaf_rn(d0, c1[0], a[4]); a[5] = __fmaf_rn(d0, c1[1], a[5]);
+                    a[6] = __fmaf_rn(d1, c1[2], a[6]); a[7] = __fmaf_rn(d1, c1[3], a[7]);
+                    if (T::MIN) { summs[mt][p][0] = __fmaf_rn(mw[p], x0.y, summs[mt][p][0]); summs[mt][p][1] = __fmaf_rn(mw[p], x1.y, summs[mt][p][1]); }
+                }
             }
         }
     }
     asm volatile("cp.async.wait_group 0;");
 
     // ---- hsum_float_8 (LC/ggml.c:608-616): ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)); lanes 2tau, 2tau+1 (+4) live in thread tau = t & 1 ----
-    const int64_t n = n_base + crow;
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+    for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {                              // token g (hh = 0) / g + 8 (hh = 1)
-            const float r_lo = __fadd_rn(acc[mt][4 + 2 * hh], acc[mt][2 * hh]);          // a_{4+2tau} + a_{2tau}
-            const float r_hi = __fadd_rn(acc[mt][5 + 2 * hh], acc[mt][1 + 2 * hh]);      // a_{5+2tau} + a_{1+2tau}
-            const float s0 = __fadd_rn(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, 1));      // (a0+a4) + (a2+a6)
-            const float s1 = __fadd_rn(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, 1));      // (a1+a5) + (a3+a7)
-            float v = __fadd_rn(s0, s1);
-            if (T::MIN) v = __fadd_rn(v, summs[mt][hh]);
-            const int64_t m = m_base + mt * 16 + g + hh * 8;
-            if ((t & 1) == 0 && m < B && n < w.N) dst[m * ldd + n] = addend ? __fadd_rn(v, addend[m * lda + n]) : v;
-        }
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {                              // token g (hh = 0) / g + 8 (hh = 1)
+                const float *a = acc[mt][p];
+                const float r_lo = __fadd_rn(a[4 + 2 * hh], a[2 * hh]);              // a_{4+2tau} + a_{2tau}
+                const float r_hi = __fadd_rn(a[5 + 2 * hh], a[1 + 2 * hh]);          // a_{5+2tau} + a_{1+2tau}
+                const float s0 = __fadd_rn(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, 1));      // (a0+a4) + (a2+a6)
+                const float s1 = __fadd_rn(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, 1));      // (a1+a5) + (a3+a7)
+                float v = __fadd_rn(s0, s1);
+                if (T::MIN) v = __fadd_rn(v, summs[mt][p][hh]);
+                const int64_t m = m_base + tg * 32 + mt * 16 + g + hh * 8;
+                const int64_t n = n_base + rg * 8 + p * 2 + (t >> 1);
+                if ((t & 1) == 0 && m < B && n < w.N) dst[m * ldd + n] = addend ? __fadd_rn(v, addend[m * lda + n]) : v;
+            }
 }
 
 // quantize_act with the quants written as fp16 (exact: |q| <= 127): same arithmetic as quantize_act_kernel (quant.cu)
@@ -214,14 +253,17 @@ __global__ void __launch_bounds__(256) quantize_act_f16_kernel(const float *__re
     const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
     const int q = __float2int_rn(__fmul_rn(v, id));
     const int isum = warp_sum(q);
-    xh[blk * QK + lane] = __int2half_rn(q);
+    // xh is stored in MMA A-fragment order (see the kernel header): [16-token tile][block][chunk c][g][t]{tok g: j0 j1 | tok g+8: j0 j1 | tok g: j2 j3 | tok g+8: j2 j3}
+    // for element e = 16c + 4t + j of token 16*tile + 8*h + g
+    const int c = lane >> 4, tt = (lane >> 2) & 3, j = lane & 3, gg = (int)(row & 7), h = (int)((row >> 3) & 1);
+    xh[((row >> 4) * nbk + b) * 512 + c * 256 + (gg * 4 + tt) * 8 + (j >> 1) * 4 + h * 2 + (j & 1)] = __int2half_rn(q);
     if (lane == 0) ds[blk] = Q81 ? make_float2(d, __fmul_rn(d, (float)isum)) : make_float2(__half2float(__float2half_rn(d)), (float)isum);
 }
 
 template <int TYPE>
 void launch_xmma(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st) {
     using T = Xm<TYPE>;
-    constexpr int smem = XST * T::STAGE;
+    constexpr int smem = T::SMEM;
     static bool set = false;
     if (!set) { B200_CHECK(cudaFuncSetAttribute(mm_exact_mma_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
     dim3 grid((unsigned)((w.N + XN - 1) / XN), (unsigned)((B + XM - 1) / XM));

@@ -38,6 +38,8 @@ void mul_mat_q_simple(const QWeight &w, const int8_t *xq, const float2 *xds, flo
 void mul_mat_q_exact(const QWeight &w, const int8_t *xq, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 
 // ---- exact_mma.cu : bit-exact batched mat-mul with the block dots on tensor cores (block-diagonal f16 MMA) --------------------------
+// xh = fp16 quants in the MMA-fragment tile order of exact_mma.cu (16-token tiles: allocate xh_bytes(K, B))
+inline size_t xh_bytes(int64_t K, int64_t B) { return (size_t)((B + 15) / 16 * 16) * (size_t)K * 2; }
 void quantize_act_f16(int vdt, const float *x, int64_t ldx, __half *xh, float2 *ds, int64_t K, int64_t B, cudaStream_t st);
 void mul_mat_q_exact_mma(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 

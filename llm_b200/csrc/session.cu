@@ -171,7 +171,7 @@ void forward(b200_session *s, int n) {
             }
             s->mega_ok = false;
         } else {
-            // default: 8 fused kernels per layer, replayed from one CUDA graph per token (decode_ops.cu)
+            // default: 7 fused kernels per layer, replayed from one CUDA graph per token (decode_ops.cu)
             int bucket = ((n_kv + 255) / 256) * 256; if (bucket > n_ctx) bucket = n_ctx;
             int nodes = 0;
             if (!s->decode_warm || (s->cfg.flags & B200_SESSION_NO_GRAPH)) {
@@ -491,7 +491,7 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMalloc(&s->xq, B * kmax));
     B200_CHECK(cudaMalloc(&s->xds, B * (kmax / QK) * sizeof(float2)));
     B200_CHECK(cudaMalloc(&s->xpack, (kmax / QK) * 64));
-    B200_CHECK(cudaMalloc(&s->xh, B * kmax * 2));
+    B200_CHECK(cudaMalloc(&s->xh, xh_bytes(kmax, B)));
     B200_CHECK(cudaMallocHost(&s->h_tokens, B * 4));
     B200_CHECK(cudaMallocHost(&s->h_logits, B * (size_t)hp.n_vocab * 4));
     B200_CHECK(cudaEventCreateWithFlags(&s->tokens_uploaded, cudaEventDisableTiming));
@@ -528,8 +528,8 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     P.xpack_d = s->xpack_d; P.xpack_f = s->xpack_f;
     B200_CHECK(cudaMalloc(&s->xpack_a, (e / QK) * 64));
     P.scratch_bytes = decode_scratch_bytes((int)e, (int)f, m->hd, (int)n_ctx);
-    B200_CHECK(cudaMalloc(&s->d_prof, 128 * sizeof(unsigned long long)));
-    B200_CHECK(cudaMemset(s->d_prof, 0, 128 * sizeof(unsigned long long)));
+    B200_CHECK(cudaMalloc(&s->d_prof, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
+    B200_CHECK(cudaMemset(s->d_prof, 0, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
     P.prof = getenv("B200_DECODE_PROF") ? s->d_prof : nullptr;
     s->mega_ok = hp.n_rot == m->hd && (m->hd == 64 || m->hd == 128) && decode_supported(P, hp.wtype);
     return s;
@@ -615,6 +615,23 @@ int b200_session_decode_profile(b200_session *s, unsigned long long *out128) {
     return B200_OK;
 }
 
+// Per-kernel timeline of the graph decode schedule (B200_DECODE_PROF=1): slot i = the i-th launch of the token;
+// out = 8 arrays of n (%globaltimer, ns): CTA begin min, CTA end max, prologue-done min, begin max, prologue-done max, first stage landed min / max,
+// last stage landed max (mat-vec kernels only for the last three).  reset != 0 re-arms the slots.
+int b200_session_decode_timeline(b200_session *s, unsigned long long *out, int n, int reset) {
+    if (!s || n < 0 || n > B200_PROF_SLOTS) return B200_ERR_BAD_ARG;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    if (out && n) {
+        for (int k = 0; k < 8; k++)
+            B200_CHECK(cudaMemcpy(out + (size_t)k * n, s->d_prof + (size_t)k * B200_PROF_SLOTS, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (reset) {                                                  // arrays 0, 2, 5 hold minima, the others maxima
+        for (int k = 0; k < 8; k++)
+            B200_CHECK(cudaMemset(s->d_prof + (size_t)k * B200_PROF_SLOTS, (k == 0 || k == 2 || k == 5) ? 0xFF : 0, B200_PROF_SLOTS * sizeof(unsigned long long)));
+    }
+    return B200_OK;
+}
+
 int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchronize(rt().stream)); return B200_OK; }
 
 void b200_session_free(b200_session *s) {
@@ -668,7 +685,7 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
     quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
     if (impl == B200_MM_AUTO) impl = B200_MM_EXACT;
     if (impl == B200_MM_EXACT_MMA) {
-        __half *xh = (__half *)R.op_arena.get((size_t)B * K * 2, st);
+        __half *xh = (__half *)R.op_arena.get((size_t)xh_bytes(K, B), st);
         quantize_act_f16(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
         mul_mat_q_exact_mma(w, xh, xds, dd, N, B, nullptr, 0, st);
     } else if (impl == B200_MM_EXACT_STREAM) {

@@ -3,6 +3,10 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef B200_PROF_SLOTS
+#define B200_PROF_SLOTS 1024
+#endif
+
 namespace b200 {
 namespace stream {
 
@@ -12,15 +16,15 @@ constexpr int SST = 4;        // ring stages of the stand-alone mat-vec kernel (
 constexpr int SCOMPUTE = 128; // 4 compute warps (4 threads per row)
 constexpr int STHREADS = SCOMPUTE + 32;   // + 1 producer warp
 
-template <int TYPE> struct St {
+template <int TYPE, int ROWS = SR, int CB = SCB> struct St {
     static constexpr int QS = (TYPE == T_Q8_0) ? 32 : 16;
     static constexpr int DM = (TYPE == T_Q4_1 || TYPE == T_Q5_1) ? 4 : 2;
     static constexpr bool QH = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
     static constexpr bool MIN = (TYPE == T_Q4_1 || TYPE == T_Q5_1);
-    static constexpr int QS_STRIDE = SCB * QS + 16;     // +16 B: the 8 rows of a warp land in different banks
-    static constexpr int DM_STRIDE = SCB * DM + 16;
-    static constexpr int QH_STRIDE = SCB * 4 + 16;
-    static constexpr int QS_BYTES = SR * QS_STRIDE, DM_BYTES = SR * DM_STRIDE, QH_BYTES = QH ? SR * QH_STRIDE : 0;
+    static constexpr int QS_STRIDE = CB * QS + 16;     // +16 B: the 8 rows of a warp land in different banks
+    static constexpr int DM_STRIDE = CB * DM + 16;
+    static constexpr int QH_STRIDE = CB * 4 + 16;
+    static constexpr int QS_BYTES = ROWS * QS_STRIDE, DM_BYTES = ROWS * DM_STRIDE, QH_BYTES = QH ? ROWS * QH_STRIDE : 0;
     static constexpr int STAGE_BYTES = QS_BYTES + DM_BYTES + QH_BYTES;
     static constexpr int RING_BYTES = SST * STAGE_BYTES;
     __host__ __device__ static constexpr int ring_bytes(int nst) { return nst * STAGE_BYTES; }
@@ -43,12 +47,14 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void *src) { asm volati
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SCOMPUTE) : "memory"); }   // the 4 compute warps only
 
-constexpr int SST_MAX = 8;
+constexpr int SST_MAX = 12;    // barrier arrays: full[12] | empty[12] in the first 192 bytes of the CTA's shared memory
 struct Ring {                 // per-CTA streaming state (lives in registers; the storage is shared memory)
     uint64_t *full, *empty;   // [nst] each
     uint8_t *base;
     uint32_t g;               // running stage counter: producer and consumers enumerate stages in the same order
     uint32_t nst;             // ring depth (<= SST_MAX)
+    uint32_t slot, phase;     // g % nst and (g / nst) & 1, kept incrementally (nst is a run-time value: no division per stage)
+    __device__ __forceinline__ void advance() { g++; if (++slot == nst) { slot = 0; phase ^= 1u; } }
 };
 
 __device__ __forceinline__ void ring_init(uint64_t *full, uint64_t *empty, int nst) {   // one thread, before a CTA-wide barrier
@@ -58,20 +64,20 @@ __device__ __forceinline__ void ring_init(uint64_t *full, uint64_t *empty, int n
 
 // One plane of a stage: SR rows x (COLS x 16 B), global row pitch src_pitch bytes, shared row pitch dst_pitch.  No divisions:
 // COLS is a power of two, a warp instruction covers 32/COLS rows (COLS <= 32) or half a row (COLS == 64).
-template <int COLS>
+template <int COLS, int ROWS = SR>
 __device__ __forceinline__ void stream_plane(uint32_t dst, int dst_pitch, const uint8_t *src, int64_t src_pitch, int cols_valid, int rows_valid, int lane) {
     if (COLS >= 32) {
 #pragma unroll 8
-        for (int rr = 0; rr < SR; rr++) {
+        for (int rr = 0; rr < ROWS; rr++) {
             const uint8_t *srow = src + (int64_t)(rr < rows_valid ? rr : rows_valid - 1) * src_pitch;      // tail tile: re-read a valid row
 #pragma unroll
             for (int k = 0; k < COLS / 32; k++) { const int cc = lane + 32 * k; if (cc < cols_valid) cp16(dst + rr * dst_pitch + cc * 16, srow + cc * 16); }
         }
     } else {
-        constexpr int RPI = 32 / COLS;
+        constexpr int RPI = COLS >= 32 ? 1 : 32 / COLS;               // (this branch is dead for COLS >= 32)
         const int r0 = lane / COLS, cc = lane % COLS;
 #pragma unroll
-        for (int it = 0; it < SR / RPI; it++) {
+        for (int it = 0; it < ROWS / RPI; it++) {
             const int rr = it * RPI + r0;
             const uint8_t *srow = src + (int64_t)(rr < rows_valid ? rr : rows_valid - 1) * src_pitch;
             if (cc < cols_valid) cp16(dst + rr * dst_pitch + cc * 16, srow + cc * 16);
@@ -82,25 +88,25 @@ __device__ __forceinline__ void stream_plane(uint32_t dst, int dst_pitch, const 
 // Producer warp: stream every row tile (tile0, tile0 + tstride, ...) of W through the ring.
 // Tiles are handed out in groups of G consecutive tiles (G = 2 lets an epilogue see 64 consecutive rows, e.g. 32 rows of w1 and the
 // matching 32 rows of w3): group g = tile0, tile0 + tstride, ... covers tiles [g*G, g*G + G).
-template <int TYPE>
+template <int TYPE, int ROWS = SR, int CB = SCB>
 __device__ __forceinline__ void produce_matvec(const QWeight &w, Ring &R, int tile0, int tstride, int lane, int G = 1) {
-    using T = St<TYPE>;
-    const int nb = (int)w.nb, nchunks = (nb + SCB - 1) / SCB, ntiles = (int)((w.N + SR - 1) / SR);
+    using T = St<TYPE, ROWS, CB>;
+    const int nb = (int)w.nb, nchunks = (nb + CB - 1) / CB, ntiles = (int)((w.N + ROWS - 1) / ROWS);
     const uint32_t ring_u32 = smem_u32(R.base);
     for (int grp = tile0; grp * G < ntiles; grp += tstride)
     for (int tile = grp * G; tile < grp * G + G && tile < ntiles; tile++) {
-        const int64_t row_base = (int64_t)tile * SR;
-        const int rows_valid = (int)(w.N - row_base < SR ? w.N - row_base : SR);
-        for (int c = 0; c < nchunks; c++, R.g++) {
-            const int s = R.g % R.nst;
-            const int b0 = c * SCB, cb = nb - b0 < SCB ? nb - b0 : SCB;
-            mbar_wait(&R.empty[s], ((R.g / R.nst) & 1) ^ 1);
+        const int64_t row_base = (int64_t)tile * ROWS;
+        const int rows_valid = (int)(w.N - row_base < ROWS ? w.N - row_base : ROWS);
+        for (int c = 0; c < nchunks; c++, R.advance()) {
+            const int s = R.slot;
+            const int b0 = c * CB, cb = nb - b0 < CB ? nb - b0 : CB;
+            mbar_wait(&R.empty[s], R.phase ^ 1u);
             const uint32_t st = ring_u32 + s * T::STAGE_BYTES;
-            stream_plane<SCB * T::QS / 16>(st, T::QS_STRIDE, w.qs + (row_base * nb + b0) * T::QS, (int64_t)nb * T::QS, cb * T::QS / 16, rows_valid, lane);
-            stream_plane<SCB * T::DM / 16>(st + T::QS_BYTES, T::DM_STRIDE, (const uint8_t *)w.dm + (row_base * nb + b0) * T::DM, (int64_t)nb * T::DM,
+            stream_plane<CB * T::QS / 16, ROWS>(st, T::QS_STRIDE, w.qs + (row_base * nb + b0) * T::QS, (int64_t)nb * T::QS, cb * T::QS / 16, rows_valid, lane);
+            stream_plane<CB * T::DM / 16, ROWS>(st + T::QS_BYTES, T::DM_STRIDE, (const uint8_t *)w.dm + (row_base * nb + b0) * T::DM, (int64_t)nb * T::DM,
                                            cb * T::DM / 16, rows_valid, lane);
             if (T::QH)
-                stream_plane<SCB * 4 / 16>(st + T::QS_BYTES + T::DM_BYTES, T::QH_STRIDE, (const uint8_t *)(w.qh + row_base * nb + b0), (int64_t)nb * 4,
+                stream_plane<CB * 4 / 16, ROWS>(st + T::QS_BYTES + T::DM_BYTES, T::QH_STRIDE, (const uint8_t *)(w.qh + row_base * nb + b0), (int64_t)nb * 4,
                                            cb * 4 / 16, rows_valid, lane);
             cp_async_arrive(&R.full[s]);
         }
@@ -110,37 +116,43 @@ __device__ __forceinline__ void produce_matvec(const QWeight &w, Ring &R, int ti
 // Compute warps: walk the AVX2 lane chains of the tiles this CTA owns.  epi(row, value) is called by ALL 128 threads once per tile
 // (value = the finished dot product of `row`, identical in the 4 threads of a quad; row may be >= w.N on the tail tile).
 template <int TYPE, class Epi>
-__device__ __forceinline__ void consume_matvec(const QWeight &w, const int4 *sx, Ring &R, int tile0, int tstride, int tid, Epi epi, int G = 1) {
+__device__ __forceinline__ void consume_matvec(const QWeight &w, const int4 *sx, Ring &R, int tile0, int tstride, int tid, Epi epi, int G = 1,
+                                               unsigned long long *prof = nullptr) {
     using T = St<TYPE>;
     const int nb = (int)w.nb, nchunks = (nb + SCB - 1) / SCB, ntiles = (int)((w.N + SR - 1) / SR);
     const int r = tid >> 2, wd = tid & 3, lane = tid & 31;
     for (int grp = tile0; grp * G < ntiles; grp += tstride)
     for (int tile = grp * G; tile < grp * G + G && tile < ntiles; tile++) {
         float a_lo = 0.f, a_hi = 0.f, summs = 0.f;
-        for (int c = 0; c < nchunks; c++, R.g++) {
-            const int s = R.g % R.nst;
+        for (int c = 0; c < nchunks; c++, R.advance()) {
+            const int s = R.slot;
             const int b0 = c * SCB, cb = nb - b0 < SCB ? nb - b0 : SCB;
-            mbar_wait(&R.full[s], (R.g / R.nst) & 1);
+            mbar_wait(&R.full[s], R.phase);
+            if (prof && tid == 0) {                                        // tuning aid (b200_session_decode_timeline): first / latest stage arrival
+                unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (R.g == 0) { atomicMin(prof + 5 * B200_PROF_SLOTS, t); atomicMax(prof + 6 * B200_PROF_SLOTS, t); }
+                atomicMax(prof + 7 * B200_PROF_SLOTS, t);
+            }
             const uint8_t *st = R.base + s * T::STAGE_BYTES;
             const uint8_t *qrow = st + r * T::QS_STRIDE, *drow = st + T::QS_BYTES + r * T::DM_STRIDE, *hrow = st + T::QS_BYTES + T::DM_BYTES + r * T::QH_STRIDE;
 #pragma unroll 8
             for (int b = 0; b < cb; b++) {
                 const int4 xp = sx[(b0 + b) * 4 + wd];
                 float dw, mw = 0.f;
-                if (T::MIN) { const __half2 dm = *(const __half2 *)(drow + b * 4); dw = __low2float(dm); mw = __high2float(dm); }
-                else dw = __half2float(*(const __half *)(drow + b * 2));
+                if (T::MIN) { const __half2 dm = *(const __half2 *)(drow + b * T::DM); dw = __low2float(dm); mw = __high2float(dm); }
+                else dw = __half2float(*(const __half *)(drow + b * T::DM));
                 int s_lo, s_hi;
                 if (TYPE == T_Q8_0) {
-                    s_lo = __dp4a(*(const int *)(qrow + b * 32 + 4 * wd), xp.x, 0);
-                    s_hi = __dp4a(*(const int *)(qrow + b * 32 + 16 + 4 * wd), xp.y, 0);
+                    s_lo = __dp4a(*(const int *)(qrow + b * T::QS + 4 * wd), xp.x, 0);
+                    s_hi = __dp4a(*(const int *)(qrow + b * T::QS + 16 + 4 * wd), xp.y, 0);
                 } else if (TYPE == T_Q4_0) {
                     // (q - 8) as a 4-bit two's complement value is q ^ 8; parked in the HIGH nibble of each byte it reads as 16*(q-8):
                     // the dp4a result is exactly 16 * sum (q-8) x, and the 1/16 rides (exactly, a power of two) in the packed d_x.
-                    const uint32_t q = *(const uint32_t *)(qrow + b * 16 + 4 * wd);
+                    const uint32_t q = *(const uint32_t *)(qrow + b * T::QS + 4 * wd);
                     s_lo = __dp4a((int)(((q << 4) ^ 0x80808080u) & 0xF0F0F0F0u), xp.x, 0);
                     s_hi = __dp4a((int)((q ^ 0x88888888u) & 0xF0F0F0F0u), xp.y, 0);
                 } else {
-                    const uint32_t q = *(const uint32_t *)(qrow + b * 16 + 4 * wd);
+                    const uint32_t q = *(const uint32_t *)(qrow + b * T::QS + 4 * wd);
                     uint32_t l = q & 0x0F0F0F0Fu, h = (q >> 4) & 0x0F0F0F0Fu;
                     if (T::QH) {
                         const uint32_t qh = *(const uint32_t *)(hrow + b * 4);
