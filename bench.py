@@ -232,7 +232,7 @@ def main():
         pk = peaks()
         prefill = {"value": N_PAST / (ms * 1e-3), "unit": "tokens/s", "ms": ms, "reps": reps, "launches": pf_launches,
                    "tensor_frac_of_bf16_sustained": fl / (ms * 1e-3) / (pk["bf16_sustained"] * 1e12),
-                   "note": "conformant (bit-exact) path: AVX2-order lane chains on dp4a; includes attention and the 2 KB token upload"}
+                   "note": "conformant (bit-exact) path: block dots on tensor cores (block-diagonal f16 MMA), AVX2-order f32 lane chains on the fp32 pipe; includes attention and the 2 KB token upload"}
         log(f"prefill@512: {ms:.2f} ms -> {prefill['value']:.0f} tok/s ({pf_launches} kernels)")
 
     # ---- non-conformant fast mode (order-free kernels), reported separately ----
@@ -337,7 +337,7 @@ def main():
                           "frac": tok_bytes / (ms_dev / steps * 1e-3) / 1e9 / pk["hbm_gbs"]},
         "clocks": clocks,
     }
-    line["conformance"] = "logits bit-identical to the reference ggml CPU path (tests/test_gpu_llama.py); decode schedule: 8 fused kernels/layer replayed from one CUDA graph"
+    line["conformance"] = "logits bit-identical to the reference ggml CPU path (tests/test_gpu_llama.py); decode schedule: 7 fused kernels/layer (attention = one cluster launch) replayed from one CUDA graph"
     if prefill:
         line["prefill"] = prefill
     if fast_mode:

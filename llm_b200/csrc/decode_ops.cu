@@ -1,15 +1,17 @@
-// llm_b200/csrc/decode_ops.cu -- the default decode schedule: 8 fused kernels per layer, replayed from ONE CUDA graph per token.
+// llm_b200/csrc/decode_ops.cu -- the default decode schedule: 7 fused kernels per layer, replayed from ONE CUDA graph per token.
 //
 //   1 norm_pack        rms_norm(x) * attn_norm -> Q8 activation records                       (llama lib.rs:183-186 + mul_mat INIT)
 //   2 mmv<QKV>         [wq|wk|wv] x, epilogue: RoPE on Q/K rows, K/V rows -> f16 cache at n_past (:190-244)
-//   3 attn_kq          KQ = K . f16(Q)                                                        (:246-265)
-//   4 attn_sv          scale + soft_max + V^T . f16(P), epilogue: quantize the merged row     (:268-307)
-//   5 mmv<RES>         wo x + inpSA                                                           (:310-314)
-//   6 norm_pack        rms_norm(inpFF) * ffn_norm                                             (:318-321)
-//   7 mmv<SILU>        [w1|w3] x (rows interleaved in 32-row pieces), epilogue: silu(w1 x) * (w3 x) quantized (:323-330)
-//   8 mmv<RES>         w2 h + inpFF                                                           (:332-334)
+//   3 attn_fused       KQ = K . f16(Q), scale + soft_max, V^T . f16(P), epilogue: quantize the merged row -- one cluster of hd/32 CTAs per
+//                      head, scores exchanged through distributed shared memory                (:246-307)
+//                      (B200_ATTN_FUSED=0: the two-kernel variant attn_kq + attn_sv)
+//   4 mmv<RES>         wo x + inpSA                                                           (:310-314)
+//   5 norm_pack        rms_norm(inpFF) * ffn_norm                                             (:318-321)
+//   6 mmv<SILU>        [w1|w3] x (rows interleaved in 32-row pieces), epilogue: silu(w1 x) * (w3 x) quantized (:323-330)
+//   7 mmv<RES>         w2 h + inpFF                                                           (:332-334)
 // Everything that depends on the position reads n_past from DEVICE memory, so the captured graph is valid for every token; the
 // last node increments it.  All arithmetic is the bit-exact arithmetic of exact.cu / rowops.cu (same device functions as decode.cu).
+// What was tried on top of this and measured slower (PDL, norm fusion, tiled weights + TMA, L2 prefetch, ...): profiles/r01_notes.md.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
