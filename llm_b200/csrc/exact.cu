@@ -155,14 +155,127 @@ __global__ void __launch_bounds__(F16X_WARPS * 32) mul_mat_f16_exact_kernel(cons
     }
 }
 
+// ---- batched version: shared-memory tiles, 4 threads per dot, 8 dots per thread --------------------------------------------------------
+// CTA = 16 src0 rows x 32 src1 rows (512 dots), 64 elements of the reduction per stage, operands staged as f32 (src0: f16 -> f32,
+// src1: f32 -> f16 -> f32, the rounding ggml_compute_forward_mul_mat applies before the f16 dot).  The 32 chains of ggml_vec_dot_f16
+// (chain l over elements k = l mod 32, sequential in k) are split over the 4 threads of a quad as l in {4u..4u+3} u {16+4u..16+4u+3}: two
+// 16-byte shared loads per operand row and step, and the reduction tree (offsets 16, 8, 4, then the two hadds) is: in-thread, quad shuffle 2,
+// quad shuffle 1, in-thread -- the reference's association exactly.  Inner loop per thread and 32-element step: 12 LDS.128 + 64 FFMA.
+constexpr int FT_A = 16, FT_B = 32, FT_K = 64, FT_STRIDE = FT_K + 4, FT_THREADS = 256;      // stride 68 floats: quads of a quarter-warp hit disjoint banks
+
+__global__ void __launch_bounds__(FT_THREADS) mul_mat_f16_tiled_kernel(const char *__restrict__ src0, int64_t ne00, int64_t ne01, int64_t ne02, int64_t nb01, int64_t nb02,
+                                                                       const char *__restrict__ src1, int64_t ne11, int64_t ne12, int64_t nb11, int64_t nb12,
+                                                                       char *__restrict__ dst, int64_t nbd1, int64_t nbd2, int causal_past) {
+    __shared__ __align__(16) float sa[2][FT_A][FT_STRIDE];
+    __shared__ __align__(16) float sb[2][FT_B][FT_STRIDE];
+    const int tid = threadIdx.x, u = tid & 3, bq = (tid >> 2) & 7, ap = tid >> 5;        // quad (ap, bq): src0 rows 2ap, 2ap+1 x src1 rows 4bq..4bq+3
+    const int64_t a0 = (int64_t)blockIdx.x * FT_A, b0 = (int64_t)blockIdx.y * FT_B, i2 = blockIdx.z;
+    if (causal_past >= 0 && a0 > causal_past + (b0 + FT_B - 1 < ne11 - 1 ? b0 + FT_B - 1 : ne11 - 1)) return;      // whole tile above the diagonal
+    const int64_t i02 = i2 / (ne12 / ne02);
+    const char *A = src0 + i02 * nb02, *Bm = src1 + i2 * nb12;
+    const int64_t np = ne00 & ~(int64_t)31;
+
+    // fill plan: src0 tile = 16 rows x 64 halves = 256 x 8 B (one per thread); src1 tile = 32 rows x 64 floats = 512 x 16 B (two per thread)
+    const int far = tid >> 4, fac = (tid & 15) * 4;                  // src0: row, first of 4 elements
+    const int fbr = tid >> 3, fbc = (tid & 7) * 4;                   // src1: rows fbr and fbr (+0) with columns fbc, fbc + 32
+    const int64_t arow = a0 + far < ne01 ? a0 + far : ne01 - 1, brow = b0 + fbr < ne11 ? b0 + fbr : ne11 - 1;
+    const __half *ga = (const __half *)(A + arow * nb01);
+    const float *gb = (const float *)(Bm + brow * nb11);
+    uint2 ra; float4 rb0, rb1;
+    auto fetch = [&](int64_t k0) {                                   // elements past np are never used by the main loop: read them as zero
+        ra = k0 + fac < np ? *(const uint2 *)(ga + k0 + fac) : make_uint2(0u, 0u);
+        rb0 = k0 + fbc < np ? *(const float4 *)(gb + k0 + fbc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rb1 = k0 + 32 + fbc < np ? *(const float4 *)(gb + k0 + 32 + fbc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto r16 = [](float v) { return __half2float(__float2half_rn(v)); };
+    auto stash = [&](int buf) {
+        const __half2 h0 = *(const __half2 *)&ra.x, h1 = *(const __half2 *)&ra.y;
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        *(float4 *)&sa[buf][far][fac] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        *(float4 *)&sb[buf][fbr][fbc] = make_float4(r16(rb0.x), r16(rb0.y), r16(rb0.z), r16(rb0.w));
+        *(float4 *)&sb[buf][fbr][32 + fbc] = make_float4(r16(rb1.x), r16(rb1.y), r16(rb1.z), r16(rb1.w));
+    };
+
+    float acc[2][4][8];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[i][j][e] = 0.f;
+
+    const int nchunks = (int)((np + FT_K - 1) / FT_K);
+    if (nchunks > 0) { fetch(0); stash(0); }
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) fetch((int64_t)(c + 1) * FT_K);
+        const int steps = np - (int64_t)c * FT_K >= FT_K ? 2 : 1;    // np is a multiple of 32
+#pragma unroll
+        for (int st = 0; st < 2; st++) {
+            if (st >= steps) break;
+            float4 av[2][2], bv[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) { av[i][0] = *(const float4 *)&sa[buf][2 * ap + i][st * 32 + 4 * u]; av[i][1] = *(const float4 *)&sa[buf][2 * ap + i][st * 32 + 16 + 4 * u]; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { bv[j][0] = *(const float4 *)&sb[buf][4 * bq + j][st * 32 + 4 * u]; bv[j][1] = *(const float4 *)&sb[buf][4 * bq + j][st * 32 + 16 + 4 * u]; }
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float *a = acc[i][j];
+                    a[0] = __fmaf_rn(av[i][0].x, bv[j][0].x, a[0]); a[1] = __fmaf_rn(av[i][0].y, bv[j][0].y, a[1]);
+                    a[2] = __fmaf_rn(av[i][0].z, bv[j][0].z, a[2]); a[3] = __fmaf_rn(av[i][0].w, bv[j][0].w, a[3]);
+                    a[4] = __fmaf_rn(av[i][1].x, bv[j][1].x, a[4]); a[5] = __fmaf_rn(av[i][1].y, bv[j][1].y, a[5]);
+                    a[6] = __fmaf_rn(av[i][1].z, bv[j][1].z, a[6]); a[7] = __fmaf_rn(av[i][1].w, bv[j][1].w, a[7]);
+                }
+        }
+        if (c + 1 < nchunks) stash(buf ^ 1);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float *a = acc[i][j];
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) r[e] = __fadd_rn(a[e], a[e + 4]);                                        // chain l += chain l + 16
+#pragma unroll
+            for (int e = 0; e < 4; e++) r[e] = __fadd_rn(r[e], __shfl_xor_sync(0xffffffffu, r[e], 2));             // l += l + 8   (valid in u = 0, 1)
+#pragma unroll
+            for (int e = 0; e < 4; e++) r[e] = __fadd_rn(r[e], __shfl_xor_sync(0xffffffffu, r[e], 1));             // l += l + 4   (valid in u = 0)
+            const float s = __fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3]));                               // the two hadds
+            const int64_t i0 = a0 + 2 * ap + i, i1 = b0 + 4 * bq + j;
+            if (u == 0 && i0 < ne01 && i1 < ne11 && !(causal_past >= 0 && i0 > causal_past + i1)) {
+                double sumf = (double)s;
+                if (np < ne00) {                                                                                   // leftovers: double += (double)(f32 product)
+                    const __half *al = (const __half *)(A + i0 * nb01);
+                    const float *bl = (const float *)(Bm + i1 * nb11);
+                    for (int64_t k = np; k < ne00; ++k) sumf += (double)__fmul_rn(__half2float(al[k]), r16(bl[k]));
+                }
+                *(float *)(dst + i2 * nbd2 + i1 * nbd1 + i0 * 4) = (float)sumf;
+            }
+        }
+}
+
 void mul_mat_f16_exact(const __half *src0, int64_t ne00, int64_t ne01, int64_t ne02, int64_t nb01, int64_t nb02,
                        const float *src1, int64_t ne11, int64_t ne12, int64_t nb11, int64_t nb12,
                        float *dst, int64_t nbd1, int64_t nbd2, int causal_past, cudaStream_t st) {
     if (ne01 == 0 || ne11 == 0 || ne12 == 0) return;
     B200_ASSERT(ne12 % ne02 == 0 && ne11 <= 65535 && ne12 <= 65535);
-    dim3 grid((unsigned)((ne01 + F16X_WARPS - 1) / F16X_WARPS), (unsigned)ne11, (unsigned)ne12);
-    mul_mat_f16_exact_kernel<<<grid, F16X_WARPS * 32, 0, st>>>((const char *)src0, ne00, ne01, ne02, nb01, nb02, (const char *)src1, ne11, ne12, nb11, nb12,
-                                                               (char *)dst, nbd1, nbd2, causal_past);
+    // the tiled kernel wants 8-byte aligned src0 rows and 16-byte aligned src1 rows; a handful of src1 rows is cheaper one warp per dot
+    const bool aligned = ((uintptr_t)src0 % 8 == 0) && nb01 % 8 == 0 && nb02 % 8 == 0 && ((uintptr_t)src1 % 16 == 0) && nb11 % 16 == 0 && nb12 % 16 == 0;
+    if (ne11 >= 8 && aligned) {
+        dim3 grid((unsigned)((ne01 + FT_A - 1) / FT_A), (unsigned)((ne11 + FT_B - 1) / FT_B), (unsigned)ne12);
+        mul_mat_f16_tiled_kernel<<<grid, FT_THREADS, 0, st>>>((const char *)src0, ne00, ne01, ne02, nb01, nb02, (const char *)src1, ne11, ne12, nb11, nb12,
+                                                              (char *)dst, nbd1, nbd2, causal_past);
+    } else {
+        dim3 grid((unsigned)((ne01 + F16X_WARPS - 1) / F16X_WARPS), (unsigned)ne11, (unsigned)ne12);
+        mul_mat_f16_exact_kernel<<<grid, F16X_WARPS * 32, 0, st>>>((const char *)src0, ne00, ne01, ne02, nb01, nb02, (const char *)src1, ne11, ne12, nb11, nb12,
+                                                                   (char *)dst, nbd1, nbd2, causal_past);
+    }
     B200_CHECK(cudaGetLastError());
 }
 
