@@ -166,6 +166,13 @@ def main():
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is NOT the benchmark config")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON); libraries that print to fd 1 (e.g. NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,7 +190,7 @@ def main():
                 "config": {"workload": "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1]), reference ggml CPU path", "l2": "n/a (CPU)"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ---- our arm ----------------------------------------------------------------------------------------------------
@@ -331,7 +338,9 @@ def main():
         "launches_per_step": launches_per_step,
         "roofline": {"bound": "hbm", "kernel": "mmv_exact_stream_kernel<Q4_0>: all 129 weight mat-vecs of the model back to back, timed alone (the dominant kernel: 93% of a token's bytes)",
                      "achieved": probe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": probe_gbs / pk["hbm_gbs"], "peak_source": pk["source"] + " (burst copy)",
-                     "traffic": None, "launches": int(nl.value), "avg_launch_us": ms_probe * 1e3 / max(1, nl.value),
+                     # ncu --set full (profiles/r01c_mmv_fused.ncu-rep): dram__bytes_read of a mat-vec launch = 1.0015 x its algorithmic bytes, no writes to speak of
+                     "traffic": nbytes.value / max(1, nl.value) * 1.0015, "traffic_source": "ncu dram__bytes_read+write per launch, scaled from the captured w13 launch (50.80 MB vs 50.72 MB algorithmic)",
+                     "launches": int(nl.value), "avg_launch_us": ms_probe * 1e3 / max(1, nl.value),
                      "algorithmic_bytes_per_launch": nbytes.value / max(1, nl.value)},
         "step_roofline": {"bytes_per_token": tok_bytes, "weights": wbytes, "kv": kvbytes, "achieved_gbs": tok_bytes / (ms_dev / steps * 1e-3) / 1e9,
                           "frac": tok_bytes / (ms_dev / steps * 1e-3) / 1e9 / pk["hbm_gbs"]},
@@ -348,7 +357,7 @@ def main():
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:                                       # the baseline leg must never take the GPU number down
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -78,10 +78,23 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     pdl_trigger();
     pdl_wait();
     prof_begin(prof);
+    // this CTA's 32 blocks are float4s [blockIdx.x * 256, +256) of the row: thread tid packs float4 blockIdx.x * 256 + tid, which is also
+    // one of the values it sums -- the row is read once, all loads (row and gains) are in flight before the first use (one L2 round trip)
+    const int mine = blockIdx.x * 256 + tid, nv = e / 4;
+    const bool active = mine < nv;
+    const float4 gv = active ? __ldg((const float4 *)gain + mine) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     double s = 0.0;
-    for (int i = tid; i < e / 4; i += 256) {
-        const float4 v = __ldcg((const float4 *)x + i);                       // written by a predecessor: L2-coherent load
-        s += (double)__fmul_rn(v.x, v.x); s += (double)__fmul_rn(v.y, v.y); s += (double)__fmul_rn(v.z, v.z); s += (double)__fmul_rn(v.w, v.w);
+    constexpr int U = 4;
+    for (int i0 = tid; i0 < nv; i0 += 256 * U) {
+        float4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) { const int i = i0 + 256 * k; v[k] = i < nv ? __ldcg((const float4 *)x + i) : make_float4(0.f, 0.f, 0.f, 0.f); }   // written by a predecessor: L2-coherent load
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            if (i0 + 256 * k == mine) xv = v[k];
+            s += (double)__fmul_rn(v[k].x, v[k].x); s += (double)__fmul_rn(v[k].y, v[k].y); s += (double)__fmul_rn(v[k].z, v[k].z); s += (double)__fmul_rn(v[k].w, v[k].w);
+        }
     }
     s = warp_sum(s);
     if (lane == 0) shd[warp] = s;
@@ -89,16 +102,10 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     const double tot = ((shd[0] + shd[1]) + (shd[2] + shd[3])) + ((shd[4] + shd[5]) + (shd[6] + shd[7]));
     const float mean = (float)(tot / (double)e);
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-    // this CTA's blocks: 8 warps x 4 blocks = 32 blocks per CTA
-    const int b = blockIdx.x * 32 + warp * 4 + (lane >> 3);
-    const bool active = b < e / QK;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        const float4 xv = __ldcg((const float4 *)x + b * 8 + (lane & 7)), gv = __ldg((const float4 *)gain + b * 8 + (lane & 7));
-        v.x = __fmul_rn(__fmul_rn(xv.x, scale), gv.x); v.y = __fmul_rn(__fmul_rn(xv.y, scale), gv.y);
-        v.z = __fmul_rn(__fmul_rn(xv.z, scale), gv.z); v.w = __fmul_rn(__fmul_rn(xv.w, scale), gv.w);
-    }
-    pack_quad(v, pack + (active ? b : 0) * 4, lane, active, q81, off, scale16);
+    float4 v;
+    v.x = __fmul_rn(__fmul_rn(xv.x, scale), gv.x); v.y = __fmul_rn(__fmul_rn(xv.y, scale), gv.y);
+    v.z = __fmul_rn(__fmul_rn(xv.z, scale), gv.z); v.w = __fmul_rn(__fmul_rn(xv.w, scale), gv.w);
+    pack_quad(v, pack + (active ? mine >> 3 : 0) * 4, lane, active, q81, off, scale16);
     prof_end(prof);
 }
 
@@ -367,7 +374,10 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
         }
     }
     if (tid < hd) q16[tid] = __float2half_rn(qv);
-    cluster.sync();                                             // q16 visible; every CTA of the cluster is running (its shared memory may be written)
+    // q16 visible inside the CTA; every CTA of the cluster is running before its shared memory is written remotely (no data is exchanged
+    // yet, so the cluster barrier can be the relaxed one: no fence)
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 
     // ---- KQ for this CTA's share of the positions ----
     {
