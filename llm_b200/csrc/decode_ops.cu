@@ -28,9 +28,11 @@ using namespace stream;
 
 namespace {
 
-// Programmatic dependent launch: every kernel of the chain lets its successor start launching at once (`pdl_trigger`) and touches nothing
-// a predecessor writes (and writes nothing at all) before `pdl_wait`.  What runs ahead of the wait is the part that only reads the constant
-// weights: the producer warp of the next mat-vec fills its ring while the previous kernels drain, so HBM stays busy across kernel boundaries.
+// Programmatic dependent launch.  Every kernel of the chain touches nothing a predecessor writes (and writes nothing at all) before
+// `pdl_wait`; what runs ahead of the wait only reads the constant weights (the producer warp of the next mat-vec fills its ring).
+// WHERE the dependents are released matters (B200, LLaMA-7B decode, ms/token): trigger at kernel entry 2.41 (the successors sit on SM
+// resources the running kernel's tail needs), no PDL 1.757, trigger after the last tile is consumed 1.729, trigger from the producer warp
+// as soon as every byte of the CTA is requested 1.705 -> that is the default.
 // tuning aid: per-launch timeline (DecodeParams::prof), see b200_session_decode_timeline
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void prof_begin(unsigned long long *p) { if (p && threadIdx.x == 0) { const unsigned long long t = gtime(); atomicMin(p, t); atomicMax(p + 3 * B200_PROF_SLOTS, t); } }
@@ -40,11 +42,10 @@ __device__ __forceinline__ void prof_end(unsigned long long *p) { if (p && threa
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Measured on B200 (r01e): programmatic edges cost more than they hide here (2.02 -> 2.11 ms/token with bit 0, 2.41 with both), so the default is off.
-// B200_PDL: bit 0 = the weight mat-vecs are launched as programmatic dependents, bit 1 = the small kernels between them too
+// B200_PDL: bit 0 = the weight mat-vecs are launched as programmatic dependents, bit 1 = the small kernels between them too (default 3)
 int pdl_mask() {
     static int mask = -1;
-    if (mask < 0) { const char *e = getenv("B200_PDL"); mask = e ? atoi(e) : 0; }
+    if (mask < 0) { const char *e = getenv("B200_PDL"); mask = e ? atoi(e) : 3; }
     return mask;
 }
 
@@ -75,7 +76,6 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
                                                         int e, float eps, int q81, int off, int scale16, unsigned long long *prof) {
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_trigger();
     pdl_wait();
     prof_begin(prof);
     // this CTA's 32 blocks are float4s [blockIdx.x * 256, +256) of the row: thread tid packs float4 blockIdx.x * 256 + tid, which is also
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     const double tot = ((shd[0] + shd[1]) + (shd[2] + shd[3])) + ((shd[4] + shd[5]) + (shd[6] + shd[7]));
     const float mean = (float)(tot / (double)e);
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+    pdl_trigger();                                              // late: the successor's CTAs start while this grid drains
     float4 v;
     v.x = __fmul_rn(__fmul_rn(xv.x, scale), gv.x); v.y = __fmul_rn(__fmul_rn(xv.y, scale), gv.y);
     v.z = __fmul_rn(__fmul_rn(xv.z, scale), gv.z); v.w = __fmul_rn(__fmul_rn(xv.w, scale), gv.w);
@@ -122,11 +123,13 @@ struct MmvArgs {
     int q81, off, scale16;
     int *n_past_inc;              // EPI_LOGITS: the last node of the token increments InferenceSession::n_past on the device
     int nst;                      // ring depth chosen by launch_mmv
+    int pdl_early;                // trigger the dependents from the producer warp once every byte is requested (B200_PDL_EARLY, default 1)
     unsigned long long *prof;
 };
 
 template <int TYPE, int EPI>
 __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, const MmvArgs A) {
+    const bool pdl_early = A.pdl_early != 0;
     using T = St<TYPE>;
     extern __shared__ __align__(128) uint8_t smem[];
     Ring R{(uint64_t *)smem, (uint64_t *)smem + SST_MAX, smem + 256, 0u, (uint32_t)A.nst};
@@ -135,9 +138,12 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
     constexpr int G = EPI == EPI_SILU ? 2 : 1;
     prof_begin(A.prof);
     if (tid == 0) ring_init(R.full, R.empty, A.nst);
-    pdl_trigger();
     __syncthreads();
-    if (tid >= SCOMPUTE) { produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31, G); return; }   // weights only: runs ahead of the predecessors
+    if (tid >= SCOMPUTE) {                                      // weights only: runs ahead of the predecessors
+        produce_matvec<TYPE>(w, R, blockIdx.x, gridDim.x, tid & 31, G);
+        if (pdl_early) pdl_trigger();                           // every byte of this CTA is requested: let the successor's CTAs take the free slots
+        return;
+    }
     pdl_wait();
     for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
             compute_sync();
         }, G, A.prof);
     }
+    pdl_trigger();                                              // late: this CTA has consumed its last tile
     prof_end(A.prof);
 }
 
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
     __half *p16 = (__half *)(sm + (size_t)n_ctx * 4);
     __half *q16 = p16 + n_ctx;
     __half *vs = (__half *)(sm + (((size_t)n_ctx * 6 + (size_t)hd * 2 + 127) & ~(size_t)127));
+    pdl_wait();
     float qv = 0.f;
     if (tid < hd) qv = __ldcg(q + h * hd + tid);               // in flight together with the n_past load (hd <= 256 = ATH)
     const int n_kv = __ldcg(n_past) + 1;
@@ -434,6 +442,7 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
+    pdl_trigger();
     // ---- KQV: 32 channels x 4 threads ----
     if (tid < 128) {
         const int col = tid >> 2;
@@ -489,6 +498,7 @@ void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
     for (int c = base + 1; c <= depth_cap && c <= chunks; c++)
         if (occ[c] > 0 && (int64_t)sms * occ[c] >= need) nst = c;
     A.nst = nst;
+    { static int pe = -1; if (pe < 0) { const char *e = getenv("B200_PDL_EARLY"); pe = e ? atoi(e) : 1; } A.pdl_early = pe; }
     const int64_t slots = (int64_t)sms * occ[nst];
     launch_k<1>(mmv_fused_kernel<TYPE, EPI>, dim3((unsigned)(groups < slots ? groups : slots)), dim3(STHREADS), (size_t)smem_of(nst), st, w, A);
 }
@@ -518,10 +528,12 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
         if (fused_attn) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(P.n_head * (P.hd / 32)); cfg.blockDim = dim3(ATH); cfg.dynamicSmemBytes = fa_smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
+            cudaLaunchAttribute at[2];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = P.hd / 32; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
             B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
                                           (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, q81, off, s16, pr()));
             n++;
