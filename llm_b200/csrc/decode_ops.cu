@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
                                                         int e, float eps, int q81, int off, int scale16, unsigned long long *prof) {
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
     pdl_wait();
     prof_begin(prof);
     // this CTA's 32 blocks are float4s [blockIdx.x * 256, +256) of the row: thread tid packs float4 blockIdx.x * 256 + tid, which is also
@@ -102,7 +103,6 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     const double tot = ((shd[0] + shd[1]) + (shd[2] + shd[3])) + ((shd[4] + shd[5]) + (shd[6] + shd[7]));
     const float mean = (float)(tot / (double)e);
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-    pdl_trigger();                                              // late: the successor's CTAs start while this grid drains
     float4 v;
     v.x = __fmul_rn(__fmul_rn(xv.x, scale), gv.x); v.y = __fmul_rn(__fmul_rn(xv.y, scale), gv.y);
     v.z = __fmul_rn(__fmul_rn(xv.z, scale), gv.z); v.w = __fmul_rn(__fmul_rn(xv.w, scale), gv.w);
@@ -352,7 +352,7 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const int4 &a, const int4 
 constexpr int ATH = 256;
 __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, const __half *__restrict__ Vl,
                                                          int4 *__restrict__ xpack_out, const int *__restrict__ n_past, const uint16_t *__restrict__ lut_exp,
-                                                         float kq_scale, int hd, int n_head, int n_head_kv, int gqa, int n_ctx, int q81, int off, int scale16,
+                                                         float kq_scale, int hd, int n_head, int n_head_kv, int gqa, int n_ctx, int nlay, int q81, int off, int scale16,
                                                          unsigned long long *prof) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -363,11 +363,14 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
     const int per_head = hd / 32, h = blockIdx.x / per_head, part = blockIdx.x - h * per_head, c0 = part * 32;
     const int hk = h / (n_head / n_head_kv);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, u = tid & 3;
-    const int vstride = n_ctx + 32;                             // halves; (n_ctx + 32) * 2 B = 64 B mod 128 B: the two columns of a quarter-warp hit different banks
+    // shared-memory layout for nlay >= n_kv positions (the context bucket the graph was captured for, a multiple of 64: small enough that the
+    // next mat-vec's CTAs fit beside this kernel's and stream their weights while it runs)
+    const int vstride = nlay + 32;                              // halves; (nlay + 32) * 2 B = 64 B mod 128 B: the two columns of a quarter-warp hit different banks
     float *sc = (float *)sm;
-    __half *p16 = (__half *)(sm + (size_t)n_ctx * 4);
-    __half *q16 = p16 + n_ctx;
-    __half *vs = (__half *)(sm + (((size_t)n_ctx * 6 + (size_t)hd * 2 + 127) & ~(size_t)127));
+    __half *p16 = (__half *)(sm + (size_t)nlay * 4);
+    __half *q16 = p16 + nlay;
+    __half *vs = (__half *)(sm + (((size_t)nlay * 6 + (size_t)hd * 2 + 127) & ~(size_t)127));
+    pdl_trigger();                                              // the successor (wo) only needs shared memory beside us: let it prefetch its tiles now
     pdl_wait();
     float qv = 0.f;
     if (tid < hd) qv = __ldcg(q + h * hd + tid);               // in flight together with the n_past load (hd <= 256 = ATH)
@@ -442,7 +445,6 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
-    pdl_trigger();
     // ---- KQV: 32 channels x 4 threads ----
     if (tid < 128) {
         const int col = tid >> 2;
@@ -512,8 +514,9 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
     // attention: one cluster launch per layer (default) or the two-kernel variant (B200_ATTN_FUSED=0, or head sizes a cluster cannot cover)
     static const bool fused_env = !(getenv("B200_ATTN_FUSED") && getenv("B200_ATTN_FUSED")[0] == '0');
-    const size_t fa_smem = (((size_t)P.n_ctx * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (P.n_ctx + 32) * 2;
-    const bool fused_attn = fused_env && P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 32 == 0 && fa_smem <= 227 * 1024;
+    const int nlay = (n_kv_bucket + 63) / 64 * 64;
+    const size_t fa_smem = (((size_t)nlay * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (nlay + 32) * 2;
+    const bool fused_attn = fused_env && P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024;
     static size_t fa_set = 48 * 1024;
     if (fused_attn && fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
     const size_t sv_smem = (size_t)P.n_ctx * 6 + 32 * KC * 2 + 32 * 32 * 2;
@@ -535,7 +538,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
             at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
             B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
-                                          (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, q81, off, s16, pr()));
+                                          (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, nlay, q81, off, s16, pr()));
             n++;
         } else {
             launch_k(P.hd == 128 ? attn_kq_kernel<128> : attn_kq_kernel<64>, dim3((n_kv_bucket + 63) / 64, P.n_head), dim3(128), 0, st,
