@@ -200,7 +200,9 @@ def test_seam_mul_mat_f16_bit_exact(ctx, orc):
     """the attention mat-muls: F16 src0 (KV cache views), f32 src1 rounded to fp16, ggml_vec_dot_f16 operation order"""
     from llm_b200 import ggml
     rng = np.random.default_rng(21)
-    for k, rows, n, heads in ((128, 70, 5, 4), (64, 33, 1, 3), (45, 64, 7, 2), (513, 128, 1, 2), (96, 16, 3, 1)):
+    # n < 8 or unaligned rows: one warp per dot; otherwise the shared-memory tiled kernel (16 x 32 tiles, ragged edges, leftovers k % 32)
+    for k, rows, n, heads in ((128, 70, 5, 4), (64, 33, 1, 3), (45, 64, 7, 2), (513, 128, 1, 2), (96, 16, 3, 1),
+                              (128, 70, 40, 4), (96, 33, 9, 2), (100, 24, 16, 2), (64, 17, 33, 1), (516, 20, 12, 1)):
         a = rng.standard_normal((heads, rows, k)).astype(np.float16)
         b = (rng.standard_normal((heads, n, k)) * 2).astype(np.float32)
         at = ctx.transfer_to_gpu(ctx.new_tensor(ggml.F16, [k, rows, heads], a))
