@@ -57,6 +57,13 @@ enum {                            /* return codes (0 = ok).  CUDA failures print
     B200_ERR_UNKNOWN_TENSOR = -3, /* LoadError::UnknownTensor */
     B200_ERR_TENSOR_SHAPE = -4,   /* LoadError::TensorWrongSize */
     B200_ERR_NOT_LOADED = -5,
+    /* file loading (ggml::format::LoadError, crates/ggml/src/format/loader.rs:38-70; llm_base::LoadError) */
+    B200_ERR_IO = -10,
+    B200_ERR_INVALID_MAGIC = -11,
+    B200_ERR_INVALID_FORMAT_VERSION = -12,
+    B200_ERR_INVARIANT_BROKEN = -13,        /* n_dims > 2, negative sizes, Q4_0/Q4_1 rows with ne0 % 64 != 0 */
+    B200_ERR_UNSUPPORTED_ELEMENT_TYPE = -14,
+    B200_ERR_QUANTIZATION_VERSION = -15,    /* quantized tensors need quantization version 2 (llm-base loader.rs:481-484) */
 };
 
 int  b200_init(int device);                                   /* accelerator::initialize(device), accelerator/mod.rs:68-77 */
@@ -72,7 +79,35 @@ int  b200_model_synthesize(b200_model *m, uint64_t seed);
 int  b200_model_read_tensor(b200_model *m, const char *name, void *host_out, size_t nbytes);
 size_t b200_model_tensor_nbytes(b200_model *m, const char *name);
 size_t b200_model_weight_bytes(b200_model *m);                /* bytes of all 2-D weights resident in HBM */
+int  b200_model_is_loaded(b200_model *m);                     /* every tensor of the architecture has been loaded */
 void b200_model_free(b200_model *m);
+
+/* ---- GGML / GGMF / GGJT model files: ggml::format::load / save, llm::load::<Llama> -------------------------
+ * The parser is host-only (mmap; usable without a GPU).  Offsets are from the start of the file; GGJT tensor data is 32-byte aligned. */
+typedef struct b200_ggml_file b200_ggml_file;
+typedef struct {
+    char     name[96];
+    int32_t  type, n_dims;        /* enum ggml_type; n_dims <= 2 */
+    int64_t  ne[2];               /* ne[0] = row length */
+    uint64_t offset, nbytes;      /* TensorLoadInfo::start_offset, calc_size() */
+} b200_ggml_tensor_info;
+
+b200_ggml_file *b200_ggml_open(const char *path, int *err);                     /* NULL + *err on LoadError */
+void    b200_ggml_close(b200_ggml_file *f);
+int     b200_ggml_container(const b200_ggml_file *f, uint32_t *magic, uint32_t *version);      /* ContainerType */
+int64_t b200_ggml_n_tensors(const b200_ggml_file *f);
+int     b200_ggml_tensor(const b200_ggml_file *f, int64_t i, b200_ggml_tensor_info *out);
+const void *b200_ggml_tensor_data(const b200_ggml_file *f, int64_t i);          /* into the mapping */
+int64_t b200_ggml_n_vocab(const b200_ggml_file *f);
+int     b200_ggml_token(const b200_ggml_file *f, int64_t i, const uint8_t **bytes, uint32_t *len, float *score);
+/* llama Hyperparameters::read_ggml + FileType + the quantization-version rule; n_ff / wtype are taken from the tensor table */
+int     b200_ggml_llama_hparams(const b200_ggml_file *f, b200_llama_hparams *out, int32_t *n_mult, int32_t *llama_ftype, int32_t *quantization_version);
+/* ggml::format::save (GGJT v3) */
+int     b200_ggml_write_llama(const char *path, const b200_llama_hparams *hp, int32_t n_mult, int32_t file_type, const uint8_t *const *token_bytes, const uint32_t *token_len,
+                              const float *token_score, const b200_ggml_tensor_info *tensors, const void *const *data, int64_t n_tensors);
+/* llm::load::<Llama>(path, ModelParameters): parse + b200_llama_new + one b200_model_load_tensor per tensor, straight from the mapping;
+ * context_size / rope_* <= 0 keep the defaults (2048, 10000, 1) */
+b200_model *b200_llama_load_file(const char *path, int32_t context_size, float rope_freq_base, float rope_freq_scale, int *err);
 
 b200_session *b200_model_start_session(b200_model *m, const b200_session_config *cfg);
 /* One forward pass over `n` tokens appended at n_past (InferenceSession::compute + Llama::evaluate).  tokens: HOST int32.

@@ -12,3 +12,4 @@ from . import ggml  # noqa: F401
 # enum ggml_type values of the five block formats on the hot path (LC/ggml.h:262-285)
 Q4_0, Q4_1, Q5_0, Q5_1, Q8_0 = 2, 3, 6, 7, 8
 F32, F16 = 0, 1
+from . import loader  # noqa: F401

@@ -19,6 +19,11 @@ class LlamaHparams(C.Structure):
                 ("context_size", C.c_int32), ("rope_freq_base", C.c_float), ("rope_freq_scale", C.c_float)]
 
 
+class GgmlTensorInfo(C.Structure):
+    """b200_ggml_tensor_info <- TensorLoadInfo, crates/ggml/src/format/loader.rs:72-86."""
+    _fields_ = [("name", C.c_char * 96), ("type", C.c_int32), ("n_dims", C.c_int32), ("ne", C.c_int64 * 2), ("offset", C.c_uint64), ("nbytes", C.c_uint64)]
+
+
 class SessionConfig(C.Structure):
     """b200_session_config <- InferenceSessionConfig, crates/llm-base/src/inference_session.rs:799-841."""
     _fields_ = [("n_batch", C.c_int32), ("flags", C.c_int32)]
@@ -68,6 +73,23 @@ def lib():
     L.b200_timing_end_ms.restype = C.c_float
     L.b200_session_probe_matvec.restype = C.c_float
     L.b200_session_probe_matvec.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(C.c_double)]
+    L.b200_model_is_loaded.argtypes = [vp]
+    L.b200_ggml_open.restype = vp
+    L.b200_ggml_open.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.b200_ggml_close.argtypes = [vp]
+    L.b200_ggml_container.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.b200_ggml_n_tensors.restype = i64
+    L.b200_ggml_n_tensors.argtypes = [vp]
+    L.b200_ggml_tensor.argtypes = [vp, i64, C.POINTER(GgmlTensorInfo)]
+    L.b200_ggml_tensor_data.restype = vp
+    L.b200_ggml_tensor_data.argtypes = [vp, i64]
+    L.b200_ggml_n_vocab.restype = i64
+    L.b200_ggml_n_vocab.argtypes = [vp]
+    L.b200_ggml_token.argtypes = [vp, i64, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    L.b200_ggml_llama_hparams.argtypes = [vp, C.POINTER(LlamaHparams), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.b200_ggml_write_llama.argtypes = [C.c_char_p, C.POINTER(LlamaHparams), i32, i32, vp, vp, vp, C.POINTER(GgmlTensorInfo), vp, i64]
+    L.b200_llama_load_file.restype = vp
+    L.b200_llama_load_file.argtypes = [C.c_char_p, i32, C.c_float, C.c_float, C.POINTER(C.c_int)]
     L.b200_op_quantize_act.argtypes = [i32, vp, i64, i64, vp, vp, vp]
     L.b200_op_mul_mat.argtypes = [i32, vp, i64, i64, vp, i64, vp, i32]
     _lib = L

@@ -459,6 +459,8 @@ int b200_model_synthesize(b200_model *m, uint64_t seed) {
     return B200_OK;
 }
 
+int b200_model_is_loaded(b200_model *m) { return m && m->n_loaded == m->n_slots(); }
+
 void b200_model_free(b200_model *m) {
     if (!m) return;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
