@@ -239,7 +239,7 @@ def main():
         pk = peaks()
         prefill = {"value": N_PAST / (ms * 1e-3), "unit": "tokens/s", "ms": ms, "reps": reps, "launches": pf_launches,
                    "tensor_frac_of_bf16_sustained": fl / (ms * 1e-3) / (pk["bf16_sustained"] * 1e12),
-                   "note": "conformant (bit-exact) path: block dots on tensor cores (block-diagonal f16 MMA), AVX2-order f32 lane chains on the fp32 pipe; includes attention and the 2 KB token upload"}
+                   "note": "conformant (bit-exact) path: block dots on tensor cores (block-diagonal f16 MMA), AVX2-order f32 lane chains on the fp32 pipe; includes attention and the 2 KB token upload; lm_head on the last row only (OutputRequest without all_logits)"}
         log(f"prefill@512: {ms:.2f} ms -> {prefill['value']:.0f} tok/s ({pf_launches} kernels)")
 
     # ---- non-conformant fast mode (order-free kernels), reported separately ----

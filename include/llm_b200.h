@@ -115,6 +115,9 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
  * May be NULL (feed only).  n must be <= n_batch. */
 int  b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, float *logits_out, int32_t all_logits);
 /* feed_prompt: evaluate in chunks of n_batch; last row of logits returned */
+/* sampler hand-off: the k (<= 1024) largest logits of the last evaluated row, selected on the device -- descending logit,
+ * ties by ascending token id -- so that 8 k bytes cross PCIe instead of n_vocab floats */
+int  b200_session_top_k(b200_session *s, int32_t k, int32_t *ids_out, float *logits_out);
 int  b200_session_feed_prompt(b200_session *s, const int32_t *tokens, int32_t n, float *last_logits_out);
 /* Device-resident variant for measurements: tokens already in HBM, logits stay in HBM (no host copies, no sync) */
 int  b200_session_evaluate_device(b200_session *s, const int32_t *d_tokens, int32_t n);

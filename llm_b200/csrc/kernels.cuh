@@ -54,6 +54,8 @@ struct Luts { const uint16_t *silu, *gelu, *exp; };   // 3 x 64 Ki fp16 tables b
 const Luts &luts();                                   // uploaded on first use
 // y = x / sqrt(mean(x^2) + eps) [* gain]   (LC/ggml.c:10129-10175 + the following ggml_mul node)
 void rms_norm(const float *x, float *y, const float *gain, int64_t n, int64_t rows, float eps, cudaStream_t st);
+// the k largest of x[0..n) in descending order (ties: smaller index first); k <= 1024
+void top_k_rows(const float *x, int64_t n, int k, int32_t *ids, float *vals, cudaStream_t st);
 // y = (x - mean) / sqrt(var + 1e-5) [* gain] [+ bias]   (LC/ggml.c:10063-10111)
 void layer_norm(const float *x, float *y, const float *gain, const float *bias, int64_t n, int64_t rows, cudaStream_t st);
 // rows of nc: optional scale, optional causal mask (col > n_past + (row % nr) -> -inf), softmax through the fp16 exp table

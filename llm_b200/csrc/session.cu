@@ -68,9 +68,10 @@ struct b200_session {
     // activations (sized for n_batch rows)
     int32_t *d_tokens = nullptr;
     float *x = nullptr, *cur = nullptr, *ff = nullptr, *qkv = nullptr, *kq = nullptr, *h13 = nullptr, *hmul = nullptr, *logits = nullptr;
+    int32_t *topk = nullptr;            // 1024 ids + 1024 logits (b200_session_top_k)
     int8_t *xq = nullptr; float2 *xds = nullptr; int4 *xpack = nullptr; __half *xh = nullptr;
     // pinned host staging
-    int32_t *h_tokens = nullptr; float *h_logits = nullptr;
+    int32_t *h_tokens = nullptr; float *h_logits = nullptr; int32_t *h_topk = nullptr;
     cudaEvent_t tokens_uploaded = nullptr;   // guards reuse of h_tokens by the next evaluate()
     int last_launches = 0;
     int last_n = 0;
@@ -145,7 +146,9 @@ void matmul(b200_session *s, const QWeight &w, const float *x, float *dst, int64
     L.n += 2;
 }
 
-void forward(b200_session *s, int n) {
+// all_rows == false: only the last row goes through the final norm and the lm_head (OutputRequest without all_logits reads nothing else:
+// model/common.rs:6-39); rows are independent, so that row is bit-identical to the all-rows pass.
+void forward(b200_session *s, int n, bool all_rows = true) {
     b200_model *m = s->m;
     const b200_llama_hparams &hp = m->hp;
     cudaStream_t st = rt().stream;
@@ -255,8 +258,14 @@ void forward(b200_session *s, int n) {
         TAP(11, s->x, (size_t)n * e);
     }
     il = -1;
-    rms_norm(s->x, s->cur, m->norm, e, n, 5e-6f, st); L.n++;                                  // :343,346
-    matmul(s, m->output, s->cur, s->logits, hp.n_vocab, n, nullptr, 0, st, L, fast);           // :352
+    if (all_rows || n == 1 || s->tap_layer != -2) {
+        rms_norm(s->x, s->cur, m->norm, e, n, 5e-6f, st); L.n++;                              // :343,346
+        matmul(s, m->output, s->cur, s->logits, hp.n_vocab, n, nullptr, 0, st, L, fast);       // :352
+    } else {
+        const size_t last = (size_t)(n - 1);
+        rms_norm(s->x + last * e, s->cur + last * e, m->norm, e, 1, 5e-6f, st); L.n++;
+        matmul(s, m->output, s->cur + last * e, s->logits + last * hp.n_vocab, hp.n_vocab, 1, nullptr, 0, st, L, fast);
+    }
     s->last_launches = L.n;
     s->last_n = n;
     s->n_past += n;                                                                           // inference_session.rs:288
@@ -491,11 +500,13 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMalloc(&s->hmul, B * f * 4));
     B200_CHECK(cudaMalloc(&s->logits, B * (size_t)hp.n_vocab * 4));
     B200_CHECK(cudaMalloc(&s->xq, B * kmax));
+    B200_CHECK(cudaMalloc(&s->topk, 2048 * 4));
     B200_CHECK(cudaMalloc(&s->xds, B * (kmax / QK) * sizeof(float2)));
     B200_CHECK(cudaMalloc(&s->xpack, (kmax / QK) * 64));
     B200_CHECK(cudaMalloc(&s->xh, xh_bytes(kmax, B)));
     B200_CHECK(cudaMallocHost(&s->h_tokens, B * 4));
     B200_CHECK(cudaMallocHost(&s->h_logits, B * (size_t)hp.n_vocab * 4));
+    B200_CHECK(cudaMallocHost(&s->h_topk, 2048 * 4));
     B200_CHECK(cudaEventCreateWithFlags(&s->tokens_uploaded, cudaEventDisableTiming));
     const RopeTable &rt_ = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
     // decode kernel parameters
@@ -564,7 +575,7 @@ int b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, flo
     memcpy(s->h_tokens, tokens, (size_t)n * 4);
     B200_CHECK(cudaMemcpyAsync(s->d_tokens, s->h_tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     B200_CHECK(cudaEventRecord(s->tokens_uploaded, st));
-    forward(s, n);
+    forward(s, n, all_logits != 0);
     const size_t V = s->m->hp.n_vocab;
     if (logits_out) {
         const size_t rows = all_logits ? n : 1;
@@ -573,6 +584,23 @@ int b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, flo
         B200_CHECK(cudaStreamSynchronize(st));
         memcpy(logits_out, s->h_logits, rows * V * 4);
     }
+    return B200_OK;
+}
+
+// Sampler hand-off: the k largest logits of the last evaluated row, selected on the device; 8 k bytes cross PCIe instead of
+// n_vocab floats.  Order = descending logit, ties by ascending token id (what a stable descending sort of (id, logit) pairs yields: llm-samplers top-k).
+int b200_session_top_k(b200_session *s, int32_t k, int32_t *ids_out, float *logits_out) {
+    if (!s || !ids_out || !logits_out || k < 1 || k > 1024 || k > s->m->hp.n_vocab || s->last_n < 1) return B200_ERR_BAD_ARG;
+    cudaStream_t st = rt().stream;
+    const size_t V = s->m->hp.n_vocab;
+    int32_t *d_ids = s->topk;
+    float *d_vals = (float *)(s->topk + 1024);
+    top_k_rows(s->logits + (size_t)(s->last_n - 1) * V, (int64_t)V, k, d_ids, d_vals, st);
+    B200_CHECK(cudaMemcpyAsync(s->h_topk, d_ids, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaMemcpyAsync(s->h_topk + 1024, d_vals, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    memcpy(ids_out, s->h_topk, (size_t)k * 4);
+    memcpy(logits_out, s->h_topk + 1024, (size_t)k * 4);
     return B200_OK;
 }
 
@@ -641,10 +669,11 @@ void b200_session_free(b200_session *s) {
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     if (s->h_n_past) B200_CHECK(cudaFreeHost(s->h_n_past));
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
-    void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack, s->xh};
+    void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack, s->xh, s->topk};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));
     if (s->h_logits) B200_CHECK(cudaFreeHost(s->h_logits));
+    if (s->h_topk) B200_CHECK(cudaFreeHost(s->h_topk));
     if (s->tokens_uploaded) B200_CHECK(cudaEventDestroy(s->tokens_uploaded));
     delete s;
 }

@@ -128,6 +128,12 @@ class InferenceSession:
     def n_past(self) -> int:
         return self.L.b200_session_n_past(self._s)
 
+    def top_k(self, k: int):
+        """Sampler hand-off: (token ids, logits) of the k largest logits of the last evaluated row, selected on the device."""
+        ids, vals = np.empty(k, np.int32), np.empty(k, np.float32)
+        _check(self.L.b200_session_top_k(self._s, k, ids.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p)), "top_k")
+        return ids, vals
+
     def evaluate(self, tokens, all_logits: bool = False) -> np.ndarray:
         """Model::evaluate: one forward pass over `tokens` (<= n_batch) appended at n_past; returns logits
         ([n, n_vocab] when all_logits else the last row, which is also kept in self.last_logits)."""

@@ -68,6 +68,15 @@ class RefLib:
         L.rh_fp32_to_fp16.argtypes = [C.c_float]
         L.rh_fp16_to_fp32.restype = C.c_float
         L.rh_fp16_to_fp32.argtypes = [C.c_uint16]
+        if hasattr(L, "rh_gpt2_new"):                                   # oracle/ref_gpt2.c
+            L.rh_gpt2_new.restype = C.c_void_p
+            L.rh_gpt2_new.argtypes = [C.POINTER(RgParams)]
+            L.rh_gpt2_tensor.restype = C.c_void_p
+            L.rh_gpt2_tensor.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t)]
+            L.rh_gpt2_finalize.argtypes = [C.c_void_p]
+            L.rh_gpt2_reset.argtypes = [C.c_void_p]
+            L.rh_gpt2_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.rh_gpt2_free.argtypes = [C.c_void_p]
         L.rh_op.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                             C.c_void_p, C.c_void_p, C.c_int]
 
@@ -117,6 +126,51 @@ class RefLib:
     # ---- whole model ---------------------------------------------------------------------------
     def llama(self, hp, tensors, use_gpu=0, n_threads=4, n_batch=512):
         return RefLlama(self, hp, tensors, use_gpu, n_threads, n_batch)
+
+    def gpt2(self, hp, tensors, use_gpu=0, n_threads=4, n_batch=512):
+        return RefGpt2(self, hp, tensors, use_gpu, n_threads, n_batch)
+
+
+class RgParams(C.Structure):
+    """rg_params (oracle/ref_gpt2.c)."""
+    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "wtype", "use_gpu", "n_threads", "n_batch", "has_lm_head")]
+
+
+class RefGpt2:
+    """The reference's GPT-2 (crates/models/gpt2) on the reference ggml: CPU build = the oracle for GPT-2, seam build = the same graph over our backend."""
+
+    def __init__(self, ref, hp, tensors, use_gpu, n_threads, n_batch):
+        self.ref, self.hp = ref, dict(hp)
+        p = RgParams(**{k: int(hp[k]) for k in ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "wtype")}, use_gpu=use_gpu, n_threads=n_threads,
+                     n_batch=n_batch, has_lm_head=int("model/lm_head" in tensors))
+        self.m = ref.lib.rh_gpt2_new(C.byref(p))
+        assert self.m, "rh_gpt2_new failed"
+        for name, arr in tensors.items():
+            nb = C.c_size_t(0)
+            dst = ref.lib.rh_gpt2_tensor(self.m, name.encode(), C.byref(nb))
+            assert dst, name
+            arr = np.ascontiguousarray(arr)
+            assert arr.nbytes == nb.value, (name, arr.nbytes, nb.value)
+            C.memmove(dst, _p(arr), arr.nbytes)
+        assert ref.lib.rh_gpt2_finalize(self.m) == 0
+
+    def eval(self, tokens):
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        logits = np.empty((tokens.size, self.hp["n_vocab"]), np.float32)
+        rc = self.ref.lib.rh_gpt2_eval(self.m, _p(tokens), tokens.size, _p(logits))
+        assert rc == 0, rc
+        return logits
+
+    def close(self):
+        if self.m:
+            self.ref.lib.rh_gpt2_free(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class RefLlama:

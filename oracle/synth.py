@@ -63,3 +63,38 @@ def make_llama(hp, wtype, quantize, seed=0x5EED0000, gain=1.0):
 
 def make_tokens(hp, n, seed=0x70CE11):
     return np.random.default_rng(seed).integers(0, hp["n_vocab"], size=n, dtype=np.int32)
+
+
+# ---- GPT-2 (BASELINE.json configs[0]; tensor names of crates/models/gpt2/src/lib.rs:59-107) -------------------------------------------
+GPT2_CONFIGS = {
+    "gpt2-tiny": dict(n_vocab=320, n_ctx=64, n_embd=128, n_head=4, n_layer=2),
+    "gpt2-117m": dict(n_vocab=50257, n_ctx=1024, n_embd=768, n_head=12, n_layer=12),
+}
+
+
+def gpt2_tensor_shapes(hp, lm_head=False):
+    e, v, c = hp["n_embd"], hp["n_vocab"], hp["n_ctx"]
+    shapes = {"model/wpe": (c, e), "model/wte": (v, e), "model/ln_f/g": (e,), "model/ln_f/b": (e,)}
+    if lm_head:
+        shapes["model/lm_head"] = (v, e)
+    for i in range(hp["n_layer"]):
+        p = f"model/h{i}/"
+        shapes.update({p + "ln_1/g": (e,), p + "ln_1/b": (e,), p + "ln_2/g": (e,), p + "ln_2/b": (e,),
+                       p + "attn/c_attn/w": (3 * e, e), p + "attn/c_attn/b": (3 * e,), p + "attn/c_proj/w": (e, e), p + "attn/c_proj/b": (e,),
+                       p + "mlp/c_fc/w": (4 * e, e), p + "mlp/c_fc/b": (4 * e,), p + "mlp/c_proj/w": (e, 4 * e), p + "mlp/c_proj/b": (e,)})
+    return shapes
+
+
+def make_gpt2(hp, wtype, quantize, seed=0x6F720000, lm_head=False):
+    """2-D weights N(0, 1/K) quantized with the reference quantizer (wpe stays f32), gains 1 + 0.1 N(0,1), biases 0.01 N(0,1)."""
+    hp = dict(hp, wtype=wtype)
+    out = {}
+    for idx, (name, shp) in enumerate(gpt2_tensor_shapes(hp, lm_head).items()):
+        rng = np.random.default_rng(seed + idx)
+        if len(shp) == 1:
+            out[name] = ((1.0 if name.endswith("/g") else 0.0) + (0.1 if name.endswith("/g") else 0.01) * rng.standard_normal(shp)).astype(np.float32)
+        else:
+            n, k = shp
+            w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+            out[name] = w if name == "model/wpe" else quantize(wtype, w)
+    return hp, out

@@ -207,3 +207,26 @@ def test_7b_geometry_two_layers(orc):
         check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"7b-2l decode {i}")
         assert s.last_launches == 7 * hp["n_layer"] + 3
     s.close(); m.close()
+
+
+def test_last_row_only_lm_head_and_top_k(orc):
+    """OutputRequest without all_logits: only the last row goes through the lm_head (same bits as the all-rows pass); the sampler hand-off
+    returns the k largest logits of that row, selected on the device (descending, ties by ascending token id)."""
+    hp, tens = synth.make_llama(synth.CONFIGS["small"], B.Q4_0, orc.quantize)
+    toks = synth.make_tokens(hp, 40)
+    mo = orc.llama(hp, tens)
+    want = np.asarray(mo.eval(toks[:37]), np.float32).reshape(37, -1)
+    m, s = native(hp, tens, hp["n_ctx"], 64)
+    last = np.asarray(s.evaluate(toks[:37]), np.float32).ravel()                      # all_logits not requested
+    assert np.array_equal(last.view(np.uint32), want[-1].view(np.uint32))
+    for k in (1, 5, 40, 1024):
+        ids, vals = s.top_k(k)
+        order = np.lexsort((np.arange(want.shape[1]), -want[-1].astype(np.float64)))[:k]
+        assert np.array_equal(ids, order.astype(np.int32)), k
+        assert np.array_equal(vals.view(np.uint32), want[-1][order].view(np.uint32)), k
+    one = np.asarray(s.evaluate(toks[37:38]), np.float32).ravel()                     # decode (CUDA graph) then top-k of that row
+    ref1 = np.asarray(mo.eval(toks[37:38]), np.float32).ravel()
+    assert np.array_equal(one.view(np.uint32), ref1.view(np.uint32))
+    ids, vals = s.top_k(8)
+    assert np.array_equal(ids, np.lexsort((np.arange(ref1.size), -ref1.astype(np.float64)))[:8].astype(np.int32))
+    s.close(); m.close()
