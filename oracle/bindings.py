@@ -76,6 +76,7 @@ class RefLib:
             L.rh_gpt2_finalize.argtypes = [C.c_void_p]
             L.rh_gpt2_reset.argtypes = [C.c_void_p]
             L.rh_gpt2_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.rh_neox_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
             L.rh_gpt2_free.argtypes = [C.c_void_p]
         L.rh_op.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                             C.c_void_p, C.c_void_p, C.c_int]
@@ -130,19 +131,22 @@ class RefLib:
     def gpt2(self, hp, tensors, use_gpu=0, n_threads=4, n_batch=512):
         return RefGpt2(self, hp, tensors, use_gpu, n_threads, n_batch)
 
+    def neox(self, hp, tensors, use_gpu=0, n_threads=4, n_batch=512):
+        return RefGpt2(self, hp, tensors, use_gpu, n_threads, n_batch, arch=1)
+
 
 class RgParams(C.Structure):
     """rg_params (oracle/ref_gpt2.c)."""
-    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "wtype", "use_gpu", "n_threads", "n_batch", "has_lm_head")]
+    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "wtype", "use_gpu", "n_threads", "n_batch", "has_lm_head", "arch", "n_rot", "use_parallel_residual")]
 
 
 class RefGpt2:
     """The reference's GPT-2 (crates/models/gpt2) on the reference ggml: CPU build = the oracle for GPT-2, seam build = the same graph over our backend."""
 
-    def __init__(self, ref, hp, tensors, use_gpu, n_threads, n_batch):
-        self.ref, self.hp = ref, dict(hp)
-        p = RgParams(**{k: int(hp[k]) for k in ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "wtype")}, use_gpu=use_gpu, n_threads=n_threads,
-                     n_batch=n_batch, has_lm_head=int("model/lm_head" in tensors))
+    def __init__(self, ref, hp, tensors, use_gpu, n_threads, n_batch, arch=0):
+        self.ref, self.hp, self.arch = ref, dict(hp), arch
+        p = RgParams(arch=arch, n_rot=int(hp.get("n_rot", 0)), use_parallel_residual=int(hp.get("use_parallel_residual", 1)), **dict(**{k: int(hp[k]) for k in ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "wtype")}, use_gpu=use_gpu, n_threads=n_threads,
+                     n_batch=n_batch, has_lm_head=int("model/lm_head" in tensors)))
         self.m = ref.lib.rh_gpt2_new(C.byref(p))
         assert self.m, "rh_gpt2_new failed"
         for name, arr in tensors.items():
@@ -157,7 +161,7 @@ class RefGpt2:
     def eval(self, tokens):
         tokens = np.ascontiguousarray(tokens, np.int32)
         logits = np.empty((tokens.size, self.hp["n_vocab"]), np.float32)
-        rc = self.ref.lib.rh_gpt2_eval(self.m, _p(tokens), tokens.size, _p(logits))
+        rc = (self.ref.lib.rh_neox_eval if self.arch else self.ref.lib.rh_gpt2_eval)(self.m, _p(tokens), tokens.size, _p(logits))
         assert rc == 0, rc
         return logits
 

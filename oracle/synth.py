@@ -98,3 +98,39 @@ def make_gpt2(hp, wtype, quantize, seed=0x6F720000, lm_head=False):
             w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
             out[name] = w if name == "model/wpe" else quantize(wtype, w)
     return hp, out
+
+
+# ---- GPT-NeoX (BASELINE.json configs[4] geometry; tensor names of crates/models/gptneox/src/lib.rs:58-123) ------------------------------------
+NEOX_CONFIGS = {
+    "neox-tiny": dict(n_vocab=384, n_ctx=64, n_embd=128, n_head=4, n_layer=2, n_rot=8, use_parallel_residual=1),
+    "neox-tiny-seq": dict(n_vocab=384, n_ctx=64, n_embd=128, n_head=4, n_layer=2, n_rot=32, use_parallel_residual=0),
+    "neox-20b": dict(n_vocab=50432, n_ctx=2048, n_embd=6144, n_head=64, n_layer=44, n_rot=24, use_parallel_residual=1),
+}
+
+
+def neox_tensor_shapes(hp):
+    e, v = hp["n_embd"], hp["n_vocab"]
+    shapes = {"gpt_neox.embed_in.weight": (v, e), "gpt_neox.final_layer_norm.weight": (e,), "gpt_neox.final_layer_norm.bias": (e,), "embed_out.weight": (v, e)}
+    for i in range(hp["n_layer"]):
+        p = f"gpt_neox.layers.{i}."
+        shapes.update({p + "input_layernorm.weight": (e,), p + "input_layernorm.bias": (e,),
+                       p + "post_attention_layernorm.weight": (e,), p + "post_attention_layernorm.bias": (e,),
+                       p + "attention.query_key_value.weight": (3 * e, e), p + "attention.query_key_value.bias": (3 * e,),
+                       p + "attention.dense.weight": (e, e), p + "attention.dense.bias": (e,),
+                       p + "mlp.dense_h_to_4h.weight": (4 * e, e), p + "mlp.dense_h_to_4h.bias": (4 * e,),
+                       p + "mlp.dense_4h_to_h.weight": (e, 4 * e), p + "mlp.dense_4h_to_h.bias": (e,)})
+    return shapes
+
+
+def make_neox(hp, wtype, quantize, seed=0x4E580000):
+    hp = dict(hp, wtype=wtype)
+    out = {}
+    for idx, (name, shp) in enumerate(neox_tensor_shapes(hp).items()):
+        rng = np.random.default_rng(seed + idx)
+        if len(shp) == 1:
+            gain = name.endswith("norm.weight")
+            out[name] = ((1.0 if gain else 0.0) + (0.1 if gain else 0.01) * rng.standard_normal(shp)).astype(np.float32)
+        else:
+            n, k = shp
+            out[name] = quantize(wtype, (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32))
+    return hp, out

@@ -51,3 +51,31 @@ def test_gpt2_reference_executor_over_our_seam(name, lm_head):
         want, got = mc.eval(toks[lo:hi]), mg.eval(toks[lo:hi])
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, lo, hi, float(np.abs(got - want).max()))
     mg.close(); mc.close()
+
+
+def test_neox_graph_runs_on_the_reference_cpu(ref):
+    """GptNeoX::evaluate restated (parallel and sequential residual, rope mode 2 on n_rot < head size): builds and runs under ggml's asserts"""
+    for cfg in ("neox-tiny", "neox-tiny-seq"):
+        hp, tens = synth.make_neox(synth.NEOX_CONFIGS[cfg], B.Q5_0, ref.quantize)
+        toks = np.random.default_rng(3).integers(0, hp["n_vocab"], 12, dtype=np.int32)
+        m = ref.neox(hp, tens, n_threads=2, n_batch=16)
+        a = m.eval(toks[:11]); b = m.eval(toks[11:12])
+        assert a.shape == (11, hp["n_vocab"]) and np.isfinite(a).all() and np.isfinite(b).all() and float(np.abs(a).max()) > 1e-3
+        m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("cfg", ["neox-tiny", "neox-tiny-seq"])
+def test_neox_quant_format_sweep_over_our_seam(cfg, name):
+    """BASELINE.json configs[4] (the five block formats on GPT-NeoX) at test size: the reference executor over our seam vs its CPU build, bit for bit."""
+    t = B.QUANT_TYPES[name]
+    ref, seam = B.RefLib("ref"), B.RefLib("seam")
+    hp, tens = synth.make_neox(synth.NEOX_CONFIGS[cfg], t, ref.quantize)
+    toks = np.random.default_rng(17).integers(0, hp["n_vocab"], 30, dtype=np.int32)
+    mc = ref.neox(hp, tens, n_threads=2, n_batch=32)
+    mg = seam.neox(hp, tens, use_gpu=1, n_threads=2, n_batch=32)
+    for lo, hi in ((0, 19), (19, 20), (20, 21), (21, 30)):
+        want, got = mc.eval(toks[lo:hi]), mg.eval(toks[lo:hi])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (cfg, name, lo, hi, float(np.abs(got - want).max()))
+    mg.close(); mc.close()
