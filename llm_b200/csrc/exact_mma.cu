@@ -106,6 +106,16 @@ __global__ void __launch_bounds__(XTH, 2) mm_exact_mma_kernel(const QWeight w, c
     auto load_stage = [&](int s, int kt) {
         const uint32_t sA = smem_u + s * T::STAGE, sS = sA + T::A_BYTES, sQ = sS + T::S_BYTES, sD = sQ + T::Q_BYTES, sH = sD + T::D_BYTES;
         const int b0 = kt * XKB;
+        if (b0 + XKB <= nb) {                                          // every k-tile but possibly the last: no per-copy predicates
+            const uint8_t *src = (const uint8_t *)xh + (size_t)b0 * 1024;
+#pragma unroll
+            for (int i = 0; i < XM / 16; i++) cpa16(sA + i * (XKB * 1024) + tid * 16, src + a_off[i], 16);
+            if (tid < XM * XKB) cpa8(sS + (tid >> 2) * XS_STRIDE + (tid & 3) * 8, (const uint8_t *)xds + (size_t)b0 * 8 + s_off, 8);
+            if (tid < XN * XKB * QC) cpa16(sQ + tid * 16, w.qs + (size_t)b0 * T::QS + q_off, 16);
+            if (tid < XN * DC) cpa4(sD + tid * 4, (const uint8_t *)w.dm + (size_t)b0 * T::DM + d_off, 4);
+            if (T::QH && tid < XN * XKB) cpa4(sH + tid * 4, (const uint8_t *)w.qh + (size_t)b0 * 4 + h_off, 4);
+            return;
+        }
         {
             const int ok = b0 + (tid >> 6) < nb ? 16 : 0;                                  // 64 copies per block
             const uint8_t *src = (const uint8_t *)xh + (size_t)b0 * 1024;

@@ -153,7 +153,10 @@ int rh_gpt2_finalize(rg_model *m) {
     const rg_params *p = &m->hp;
 #ifdef GGML_USE_CUBLAS
     if (p->use_gpu) {
-        rg_to_gpu(m->wpe); if (p->arch == 0) rg_to_gpu(m->wte); rg_to_gpu(m->ln_f_g); rg_to_gpu(m->ln_f_b); rg_to_gpu(m->lm_head);
+        /* Gpt2::new transfers wte and wpe too (gpt2 lib.rs:59-60), but the reference's CUDA backend has no get_rows: ggml.c:14589 then aborts on the
+         * first node of the graph (GGML_ASSERT src0->backend == CPU), with their ggml-cuda.cu exactly as with our seam.  The two embedding tables
+         * therefore stay on the host here, as Llama::new / GptNeoX::new keep theirs (llama lib.rs:52-57, gptneox lib.rs:58). */
+        rg_to_gpu(m->ln_f_g); rg_to_gpu(m->ln_f_b); rg_to_gpu(m->lm_head);
         for (int i = 0; i < p->n_layer; i++) {
             struct ggml_tensor **ts = (struct ggml_tensor **)&m->layers[i];
             for (int k = 0; k < 12; k++) rg_to_gpu(ts[k]);
@@ -367,7 +370,7 @@ void rh_gpt2_free(rg_model *m) {
     if (!m) return;
 #ifdef GGML_USE_CUBLAS
     if (m->hp.use_gpu) {
-        rg_free_gpu(m->wpe); if (m->hp.arch == 0) rg_free_gpu(m->wte); rg_free_gpu(m->ln_f_g); rg_free_gpu(m->ln_f_b); rg_free_gpu(m->lm_head);
+        rg_free_gpu(m->ln_f_g); rg_free_gpu(m->ln_f_b); rg_free_gpu(m->lm_head);
         for (int i = 0; i < m->hp.n_layer; i++) { struct ggml_tensor **ts = (struct ggml_tensor **)&m->layers[i]; for (int k = 0; k < 12; k++) rg_free_gpu(ts[k]); }
         if (m->memory_k) { ggml_cuda_free_data(m->memory_k); ggml_cuda_free_data(m->memory_v); }
         ggml_cuda_free_scratch();

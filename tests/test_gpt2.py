@@ -40,7 +40,8 @@ def test_gpt2_batched_equals_incremental_cpu(ref):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,lm_head", [("q4_0", False), ("q5_1", True), ("q8_0", False)])
 def test_gpt2_reference_executor_over_our_seam(name, lm_head):
-    """Gpt2::evaluate with use_gpu: the reference's graph executor, every offloaded node in our kernels (LayerNorm, gelu, biases, f16 V transpose copy)."""
+    """Gpt2::evaluate with use_gpu: the reference's graph executor, every offloaded node in our kernels (LayerNorm, gelu, biases, f16 V transpose copy).
+    The embedding tables stay on the host (see oracle/ref_gpt2.c: as written, the reference aborts in ggml.c:14589 because no CUDA get_rows exists)."""
     t = B.QUANT_TYPES[name]
     ref, seam = B.RefLib("ref"), B.RefLib("seam")
     hp, tens = synth.make_gpt2(synth.GPT2_CONFIGS["gpt2-tiny"], t, ref.quantize, lm_head=lm_head)
