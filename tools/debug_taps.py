@@ -1,4 +1,7 @@
 """GPU debugging aid: per-stage comparison of the native session against the oracle on one tiny model."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere: the repo root holds llm_b200/ and oracle/
+
 import ctypes as C
 import sys
 import numpy as np

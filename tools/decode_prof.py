@@ -1,3 +1,5 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere: the repo root holds llm_b200/ and oracle/
 import ctypes as C, os, sys
 import numpy as np
 os.environ["B200_DECODE_PROF"] = "1"

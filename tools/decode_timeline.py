@@ -1,4 +1,7 @@
-"""Per-launch timeline of the graph decode schedule (tuning aid): python tools_decode_timeline.py [n_layer]"""
+"""Per-launch timeline of the graph decode schedule (tuning aid): python tools/decode_timeline.py [n_layer]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere: the repo root holds llm_b200/ and oracle/
+
 import ctypes as C, os, sys
 import numpy as np
 os.environ["B200_DECODE_PROF"] = "1"

@@ -2,4 +2,4 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q -n 4 --timeout 600 -p no:cacheprovider -k "decode_kernel" > gpurun_out/test_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_gpu.log
 grep -E "AssertionError|passed|failed|FAILED|Error|error" gpurun_out/test_gpu.log | head -20
-python tools_decode_prof.py 4 2>&1 | tail -9
+python tools/decode_prof.py 4 2>&1 | tail -9

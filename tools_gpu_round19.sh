@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools_gpt2_debug.py gpt2 2>&1 | tail -6
+timeout 120 python tools/gpt2_debug.py gpt2 2>&1 | tail -6
 for i in 1 2; do
 ( timeout 1200 python -m pytest tests -m gpu -q -n 4 --timeout 900 -p no:cacheprovider ) > gpurun_out/test_gpu_full_$i.log 2>&1
 grep -E "AssertionError|passed|failed|FAILED" gpurun_out/test_gpu_full_$i.log | head -8
