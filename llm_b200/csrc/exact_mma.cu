@@ -252,21 +252,23 @@ __global__ void __launch_bounds__(XTH, 2) mm_exact_mma_kernel(const QWeight w, c
 // quantize_act with the quants written as fp16 (exact: |q| <= 127): same arithmetic as quantize_act_kernel (quant.cu)
 template <bool Q81>
 __global__ void __launch_bounds__(256) quantize_act_f16_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__ xh, float2 *__restrict__ ds,
-                                                               int64_t nbk, int64_t total_blocks) {
+                                                               int64_t nbk, int64_t total_blocks, int64_t rows) {
     const int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blk >= total_blocks) return;
     const int lane = threadIdx.x & 31;
     const int64_t row = blk / nbk, b = blk - row * nbk;
+    // xh is stored in MMA A-fragment order (see the kernel header): [16-token tile][block][chunk c][g][t]{tok g: j0 j1 | tok g+8: j0 j1 | tok g: j2 j3 | tok g+8: j2 j3}
+    // for element e = 16c + 4t + j of token 16*tile + 8*h + g
+    const int c = lane >> 4, tt = (lane >> 2) & 3, j = lane & 3, gg = (int)(row & 7), h = (int)((row >> 3) & 1);
+    __half *out = xh + ((row >> 4) * nbk + b) * 512 + c * 256 + (gg * 4 + tt) * 8 + (j >> 1) * 4 + h * 2 + (j & 1);
+    if (row >= rows) { *out = __float2half_rn(0.f); return; }           // padding tokens of the last 16-token tile: defined (zero) operands
     const float v = x[row * ldx + b * QK + lane];
     const float amax = warp_max(fabsf(v));
     const float d = __fdiv_rn(amax, 127.f);
     const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
     const int q = __float2int_rn(__fmul_rn(v, id));
     const int isum = warp_sum(q);
-    // xh is stored in MMA A-fragment order (see the kernel header): [16-token tile][block][chunk c][g][t]{tok g: j0 j1 | tok g+8: j0 j1 | tok g: j2 j3 | tok g+8: j2 j3}
-    // for element e = 16c + 4t + j of token 16*tile + 8*h + g
-    const int c = lane >> 4, tt = (lane >> 2) & 3, j = lane & 3, gg = (int)(row & 7), h = (int)((row >> 3) & 1);
-    xh[((row >> 4) * nbk + b) * 512 + c * 256 + (gg * 4 + tt) * 8 + (j >> 1) * 4 + h * 2 + (j & 1)] = __int2half_rn(q);
+    *out = __int2half_rn(q);
     if (lane == 0) ds[blk] = Q81 ? make_float2(d, __fmul_rn(d, (float)isum)) : make_float2(__half2float(__float2half_rn(d)), (float)isum);
 }
 
@@ -284,10 +286,10 @@ void launch_xmma(const QWeight &w, const __half *xh, const float2 *xds, float *d
 }  // namespace
 
 void quantize_act_f16(int vdt, const float *x, int64_t ldx, __half *xh, float2 *ds, int64_t K, int64_t B, cudaStream_t st) {
-    const int64_t nbk = K / QK, total = nbk * B;
+    const int64_t nbk = K / QK, total = nbk * ((B + 15) / 16 * 16);      // every token slot of the last tile is written
     if (total == 0) return;
-    if (vdt == T_Q8_1) quantize_act_f16_kernel<true><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total);
-    else               quantize_act_f16_kernel<false><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total);
+    if (vdt == T_Q8_1) quantize_act_f16_kernel<true><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total, B);
+    else               quantize_act_f16_kernel<false><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total, B);
     B200_CHECK(cudaGetLastError());
 }
 

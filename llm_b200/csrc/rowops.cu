@@ -59,6 +59,7 @@ const Luts &luts() {
         B200_CHECK(cudaMemcpy(d, silu.data(), (1 << 17), cudaMemcpyHostToDevice));
         B200_CHECK(cudaMemcpy(d + (1 << 16), gelu.data(), (1 << 17), cudaMemcpyHostToDevice));
         B200_CHECK(cudaMemcpy(d + (2 << 16), ex.data(), (1 << 17), cudaMemcpyHostToDevice));
+        B200_CHECK(cudaDeviceSynchronize());   // legacy-stream copy/memset: not ordered with our non-blocking stream, and a pageable H2D cudaMemcpy may return before its DMA lands
         L.silu = d; L.gelu = d + (1 << 16); L.exp = d + (2 << 16);
     });
     return L;
@@ -304,6 +305,8 @@ const RopeTable &rope_table(int n_dims, int mode, float freq_base, float freq_sc
     float2 *d;
     B200_CHECK(cudaMalloc(&d, h.size() * sizeof(float2)));
     B200_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    B200_CHECK(cudaDeviceSynchronize());   // legacy-stream copy/memset: not ordered with our non-blocking stream, and a pageable H2D cudaMemcpy may return before its DMA lands
+    // (this was a real race: the first rope launch after a table upload read a half-written table when the GPU was shared, tests/test_seam_gpt2_neox.py)
     // an outgrown table is leaked on purpose: kernels already enqueued may still read it
     RopeTable t{d, n_pos, half, n_dims, mode & 2, freq_base, freq_scale, ne0};
     cache[key] = t;

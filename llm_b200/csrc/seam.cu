@@ -309,6 +309,7 @@ void assign_buffers_impl(ggml_tensor *tensor, bool scratch, bool force_inplace) 
         void *data;
         B200_CHECK(cudaMalloc(&data, size));
         B200_CHECK(cudaMemset(data, 0, size));
+        B200_CHECK(cudaDeviceSynchronize());   // legacy-stream copy/memset: not ordered with our non-blocking stream, and a pageable H2D cudaMemcpy may return before its DMA lands
         extra = new Extra();
         extra->data = data;
         extra->owned = true;
@@ -374,6 +375,7 @@ void ggml_cuda_transform_tensor(void *data, struct ggml_tensor *tensor) {     //
         const size_t n = nbytes(tensor);
         B200_CHECK(cudaMalloc(&e->data, n));
         B200_CHECK(cudaMemcpy(e->data, data, n, cudaMemcpyHostToDevice));
+        B200_CHECK(cudaDeviceSynchronize());   // legacy-stream copy/memset: not ordered with our non-blocking stream, and a pageable H2D cudaMemcpy may return before its DMA lands
     }
     tensor->extra = e;
 }

@@ -424,6 +424,7 @@ int b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const 
     } else {
         if (type != T_F32 || nbytes != (size_t)s.n * 4) return B200_ERR_TENSOR_SHAPE;
         B200_CHECK(cudaMemcpy(s.f, host_data, nbytes, cudaMemcpyHostToDevice));
+        B200_CHECK(cudaDeviceSynchronize());   // legacy-stream copy/memset: not ordered with our non-blocking stream, and a pageable H2D cudaMemcpy may return before its DMA lands
     }
     if (!m->loaded[id]) { m->loaded[id] = 1; m->n_loaded++; }
     return B200_OK;
@@ -545,6 +546,7 @@ b200_session *b200_model_start_session(b200_model *m, const b200_session_config 
     B200_CHECK(cudaMemset(s->d_prof, 0, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
     P.prof = getenv("B200_DECODE_PROF") ? s->d_prof : nullptr;
     s->mega_ok = hp.n_rot == m->hd && (m->hd == 64 || m->hd == 128) && decode_supported(P, hp.wtype);
+    B200_CHECK(cudaDeviceSynchronize());   // the memsets / copies above ran on the legacy stream: order them before anything on the backend's non-blocking stream
     return s;
 }
 
@@ -658,6 +660,7 @@ int b200_session_decode_timeline(b200_session *s, unsigned long long *out, int n
     if (reset) {                                                  // arrays 0, 2, 5 hold minima, the others maxima
         for (int k = 0; k < 8; k++)
             B200_CHECK(cudaMemset(s->d_prof + (size_t)k * B200_PROF_SLOTS, (k == 0 || k == 2 || k == 5) ? 0xFF : 0, B200_PROF_SLOTS * sizeof(unsigned long long)));
+        B200_CHECK(cudaDeviceSynchronize());
     }
     return B200_OK;
 }
