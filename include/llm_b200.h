@@ -92,7 +92,12 @@ typedef struct {
     uint64_t offset, nbytes;      /* TensorLoadInfo::start_offset, calc_size() */
 } b200_ggml_tensor_info;
 
-b200_ggml_file *b200_ggml_open(const char *path, int *err);                     /* NULL + *err on LoadError */
+enum { B200_ARCH_LLAMA = 0, B200_ARCH_GPT2 = 1, B200_ARCH_GPTNEOX = 2 };         /* whose Hyperparameters::read_ggml lays out the header */
+b200_ggml_file *b200_ggml_open(const char *path, int *err);                     /* LLaMA header; NULL + *err on LoadError */
+b200_ggml_file *b200_ggml_open_arch(const char *path, int32_t arch, int *err);
+/* the header words in file order: llama n_vocab n_embd n_mult n_head n_layer n_rot file_type | gpt2 n_vocab n_ctx n_embd n_head n_layer file_type n_vocab |
+ * gptneox n_vocab n_ctx n_embd n_head n_layer n_rot use_parallel_residual file_type */
+int     b200_ggml_hparams(const b200_ggml_file *f, int32_t *arch, int32_t *words8, int32_t *n_words);
 void    b200_ggml_close(b200_ggml_file *f);
 int     b200_ggml_container(const b200_ggml_file *f, uint32_t *magic, uint32_t *version);      /* ContainerType */
 int64_t b200_ggml_n_tensors(const b200_ggml_file *f);
@@ -102,7 +107,9 @@ int64_t b200_ggml_n_vocab(const b200_ggml_file *f);
 int     b200_ggml_token(const b200_ggml_file *f, int64_t i, const uint8_t **bytes, uint32_t *len, float *score);
 /* llama Hyperparameters::read_ggml + FileType + the quantization-version rule; n_ff / wtype are taken from the tensor table */
 int     b200_ggml_llama_hparams(const b200_ggml_file *f, b200_llama_hparams *out, int32_t *n_mult, int32_t *llama_ftype, int32_t *quantization_version);
-/* ggml::format::save (GGJT v3) */
+/* ggml::format::save (GGJT v3): header words verbatim (any architecture), or the LLaMA convenience form */
+int     b200_ggml_write(const char *path, const int32_t *hparam_words, int32_t n_words, int32_t n_vocab, const uint8_t *const *token_bytes, const uint32_t *token_len,
+                        const float *token_score, const b200_ggml_tensor_info *tensors, const void *const *data, int64_t n_tensors);
 int     b200_ggml_write_llama(const char *path, const b200_llama_hparams *hp, int32_t n_mult, int32_t file_type, const uint8_t *const *token_bytes, const uint32_t *token_len,
                               const float *token_score, const b200_ggml_tensor_info *tensors, const void *const *data, int64_t n_tensors);
 /* llm::load::<Llama>(path, ModelParameters): parse + b200_llama_new + one b200_model_load_tensor per tensor, straight from the mapping;

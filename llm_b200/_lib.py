@@ -77,6 +77,10 @@ def lib():
     L.b200_model_is_loaded.argtypes = [vp]
     L.b200_ggml_open.restype = vp
     L.b200_ggml_open.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.b200_ggml_open_arch.restype = vp
+    L.b200_ggml_open_arch.argtypes = [C.c_char_p, i32, C.POINTER(C.c_int)]
+    L.b200_ggml_hparams.argtypes = [vp, C.POINTER(i32), C.POINTER(i32 * 8), C.POINTER(i32)]
+    L.b200_ggml_write.argtypes = [C.c_char_p, C.POINTER(i32), i32, i32, vp, vp, vp, C.POINTER(GgmlTensorInfo), vp, i64]
     L.b200_ggml_close.argtypes = [vp]
     L.b200_ggml_container.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.b200_ggml_n_tensors.restype = i64

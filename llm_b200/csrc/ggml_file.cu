@@ -7,6 +7,8 @@
 //                                                                            n_dims <= 2, Q4_0/Q4_1 rows need ne0 % 64 == 0
 //   ContainerType::read          crates/ggml/src/lib.rs:58-86               'ggml' unversioned; 'ggmf' 1; 'ggjt' 1..3; 'ggla' 1
 //   llama Hyperparameters        crates/models/llama/src/lib.rs:425-447     7 x i32: n_vocab n_embd n_mult n_head n_layer n_rot file_type
+//   gpt2 Hyperparameters         crates/models/gpt2/src/lib.rs:394-416      6 x i32: n_vocab n_ctx n_embd n_head n_layer file_type, then n_vocab AGAIN (must match)
+//   gptneox Hyperparameters      crates/models/gptneox/src/lib.rs:431-442   8 x i32: n_vocab n_ctx n_embd n_head n_layer n_rot use_parallel_residual(0|1) file_type
 //   FileType                     crates/llm-base/src/loader.rs:32-50        file_type = quantization_version * 1000 + llama_ftype
 //   quantization version rule    crates/llm-base/src/loader.rs:459-484      0 is read as 1 (GGJT v2) / 2 (GGJT v3); quantized tensors require 2
 //   ggml::format::save           crates/ggml/src/format/saver.rs:86-160     the writer (GGJT v3)
@@ -50,7 +52,8 @@ struct b200_ggml_file {
     const uint8_t *map = nullptr;
     uint64_t size = 0;
     uint32_t magic = 0, version = 0;
-    int32_t hp[7] = {0, 0, 0, 0, 0, 0, 0};          // n_vocab n_embd n_mult n_head n_layer n_rot file_type
+    int32_t arch = 0, n_hp = 7;
+    int32_t hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // the architecture's hyperparameter words, file order (llama: n_vocab n_embd n_mult n_head n_layer n_rot file_type)
     std::vector<std::pair<uint64_t, uint32_t>> tokens;   // (offset of the bytes, length)
     std::vector<float> scores;
     std::vector<TensorInfo> tensors;
@@ -65,10 +68,12 @@ void b200_ggml_close(b200_ggml_file *f) {
     delete f;
 }
 
-b200_ggml_file *b200_ggml_open(const char *path, int *err) {
+b200_ggml_file *b200_ggml_open_arch(const char *path, int32_t arch, int *err) {
     int dummy; if (!err) err = &dummy;
+    if (arch < 0 || arch > 2) { *err = B200_ERR_BAD_ARG; return nullptr; }
     *err = B200_OK;
     b200_ggml_file *f = new b200_ggml_file();
+    f->arch = arch; f->n_hp = arch == B200_ARCH_LLAMA ? 7 : arch == B200_ARCH_GPT2 ? 7 : 8;
     auto fail = [&](int code) -> b200_ggml_file * { *err = code; b200_ggml_close(f); return nullptr; };
     f->fd = open(path, O_RDONLY);
     struct stat sb;
@@ -91,9 +96,11 @@ b200_ggml_file *b200_ggml_open(const char *path, int *err) {
                             (f->magic == MAGIC_GGLA && f->version == 1);
     if (eof || !ok_version) return fail(eof ? B200_ERR_IO : B200_ERR_INVALID_FORMAT_VERSION);
 
-    for (int i = 0; i < 7; i++) f->hp[i] = (int32_t)rd32();
+    for (int i = 0; i < f->n_hp; i++) f->hp[i] = (int32_t)rd32();
     if (eof) return fail(B200_ERR_IO);
-    for (int i = 0; i < 7; i++) if (f->hp[i] < 0) return fail(B200_ERR_INVARIANT_BROKEN);      // usize::try_from in the reference
+    for (int i = 0; i < f->n_hp; i++) if (f->hp[i] < 0) return fail(B200_ERR_INVARIANT_BROKEN);      // usize::try_from in the reference
+    if (arch == B200_ARCH_GPT2 && f->hp[6] != f->hp[0]) return fail(B200_ERR_INVARIANT_BROKEN);     // "GPT2 model expected n_vocab {} found {}"
+    if (arch == B200_ARCH_GPTNEOX && f->hp[6] > 1) return fail(B200_ERR_IO);                        // read_bool: InvalidData
 
     const bool scored = f->magic == MAGIC_GGMF || f->magic == MAGIC_GGJT;
     f->tokens.reserve((size_t)f->hp[0]);
@@ -134,6 +141,16 @@ b200_ggml_file *b200_ggml_open(const char *path, int *err) {
     return f;
 }
 
+b200_ggml_file *b200_ggml_open(const char *path, int *err) { return b200_ggml_open_arch(path, B200_ARCH_LLAMA, err); }
+
+int b200_ggml_hparams(const b200_ggml_file *f, int32_t *arch, int32_t *words8, int32_t *n_words) {
+    if (!f) return B200_ERR_BAD_ARG;
+    if (arch) *arch = f->arch;
+    if (words8) memcpy(words8, f->hp, sizeof(f->hp));
+    if (n_words) *n_words = f->n_hp;
+    return B200_OK;
+}
+
 int b200_ggml_container(const b200_ggml_file *f, uint32_t *magic, uint32_t *version) {
     if (!f) return B200_ERR_BAD_ARG;
     if (magic) *magic = f->magic;
@@ -169,7 +186,7 @@ const void *b200_ggml_tensor_data(const b200_ggml_file *f, int64_t i) {
 // LLaMA view of the header: hyperparameters + what the tensors add (n_ff = rows of feed_forward.w1, weight type = type of attention.wq),
 // and the quantization-version rule of crates/llm-base/src/loader.rs:459-484.
 int b200_ggml_llama_hparams(const b200_ggml_file *f, b200_llama_hparams *out, int32_t *n_mult, int32_t *llama_ftype, int32_t *quantization_version) {
-    if (!f || !out) return B200_ERR_BAD_ARG;
+    if (!f || !out || f->arch != B200_ARCH_LLAMA) return B200_ERR_BAD_ARG;
     memset(out, 0, sizeof(*out));
     out->n_vocab = f->hp[0]; out->n_embd = f->hp[1]; out->n_head = f->hp[3]; out->n_head_kv = f->hp[3]; out->n_layer = f->hp[4]; out->n_rot = f->hp[5];
     out->context_size = 2048; out->rope_freq_base = 10000.0f; out->rope_freq_scale = 1.0f;
@@ -189,19 +206,18 @@ int b200_ggml_llama_hparams(const b200_ggml_file *f, b200_llama_hparams *out, in
     return B200_OK;
 }
 
-// ggml::format::save for a LLaMA model: GGJT v3, tensor data 32-byte aligned.  tensors = n_tensors x {name, type, n_dims, ne, nbytes} with data[i]
-// the GGML-layout bytes; tokens/scores may be NULL (every token is then written empty with score 0).
-int b200_ggml_write_llama(const char *path, const b200_llama_hparams *hp, int32_t n_mult, int32_t file_type, const uint8_t *const *token_bytes, const uint32_t *token_len,
-                          const float *token_score, const b200_ggml_tensor_info *tensors, const void *const *data, int64_t n_tensors) {
-    if (!path || !hp || (n_tensors > 0 && (!tensors || !data))) return B200_ERR_BAD_ARG;
+// ggml::format::save: GGJT v3, the architecture's hyperparameter words verbatim, tensor data 32-byte aligned.  tensors = n_tensors x {name, type, n_dims, ne,
+// nbytes} with data[i] the GGML-layout bytes; tokens/scores may be NULL (every token is then written empty with score 0).
+int b200_ggml_write(const char *path, const int32_t *hparam_words, int32_t n_words, int32_t n_vocab, const uint8_t *const *token_bytes, const uint32_t *token_len,
+                    const float *token_score, const b200_ggml_tensor_info *tensors, const void *const *data, int64_t n_tensors) {
+    if (!path || !hparam_words || n_words < 1 || n_words > 8 || (n_tensors > 0 && (!tensors || !data))) return B200_ERR_BAD_ARG;
     FILE *fp = fopen(path, "wb");
     if (!fp) return B200_ERR_IO;
     bool ok = true;
     auto w32 = [&](uint32_t v) { ok &= fwrite(&v, 4, 1, fp) == 1; };
     w32(MAGIC_GGJT); w32(3);
-    const int32_t h[7] = {hp->n_vocab, hp->n_embd, n_mult, hp->n_head, hp->n_layer, hp->n_rot, file_type};
-    for (int i = 0; i < 7; i++) w32((uint32_t)h[i]);
-    for (int32_t i = 0; i < hp->n_vocab; i++) {
+    for (int i = 0; i < n_words; i++) w32((uint32_t)hparam_words[i]);
+    for (int32_t i = 0; i < n_vocab; i++) {
         const uint32_t len = token_len ? token_len[i] : 0;
         w32(len);
         if (len) ok &= fwrite(token_bytes[i], 1, len, fp) == len;
@@ -221,6 +237,13 @@ int b200_ggml_write_llama(const char *path, const b200_llama_hparams *hp, int32_
     }
     ok &= fclose(fp) == 0;
     return ok ? B200_OK : B200_ERR_IO;
+}
+
+int b200_ggml_write_llama(const char *path, const b200_llama_hparams *hp, int32_t n_mult, int32_t file_type, const uint8_t *const *token_bytes, const uint32_t *token_len,
+                          const float *token_score, const b200_ggml_tensor_info *tensors, const void *const *data, int64_t n_tensors) {
+    if (!hp) return B200_ERR_BAD_ARG;
+    const int32_t h[7] = {hp->n_vocab, hp->n_embd, n_mult, hp->n_head, hp->n_layer, hp->n_rot, file_type};
+    return b200_ggml_write(path, h, 7, hp->n_vocab, token_bytes, token_len, token_score, tensors, data, n_tensors);
 }
 
 // llm::load::<Llama>(path, params): parse, build the model for the file's geometry, upload every tensor from the mapping.

@@ -26,16 +26,31 @@ class LoadError(Exception):
         super().__init__(f"{what}: {self.kind}")
 
 
-class GgmlFile:
-    """A parsed container: ContainerType, LLaMA hyperparameters, vocabulary, tensor table (name, dims, type, file offset)."""
+ARCH = {"llama": 0, "gpt2": 1, "gptneox": 2}
+HPARAM_NAMES = {
+    "llama": ("n_vocab", "n_embd", "n_mult", "n_head", "n_layer", "n_rot", "file_type"),                                   # llama lib.rs:425-447
+    "gpt2": ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "file_type", "n_vocab_again"),                              # gpt2 lib.rs:394-416
+    "gptneox": ("n_vocab", "n_ctx", "n_embd", "n_head", "n_layer", "n_rot", "use_parallel_residual", "file_type"),          # gptneox lib.rs:431-442
+}
 
-    def __init__(self, path: str):
+
+class GgmlFile:
+    """A parsed container: ContainerType, the architecture's hyperparameters, vocabulary, tensor table (name, dims, type, file offset)."""
+
+    def __init__(self, path: str, arch: str = "llama"):
         self.L = _lib.lib()
         err = C.c_int(0)
-        self._f = self.L.b200_ggml_open(path.encode(), C.byref(err))
+        self.arch = arch
+        self._f = self.L.b200_ggml_open_arch(path.encode(), ARCH[arch], C.byref(err))
         if not self._f:
             raise LoadError(err.value, f"open {path}")
         self.path = path
+
+    def hyperparameters(self) -> Dict[str, int]:
+        """The header words of the file, named after the architecture's Hyperparameters struct."""
+        arch, words, n = C.c_int32(), (C.c_int32 * 8)(), C.c_int32()
+        self.L.b200_ggml_hparams(self._f, C.byref(arch), C.byref(words), C.byref(n))
+        return dict(zip(HPARAM_NAMES[self.arch], list(words)[:n.value]))
 
     @property
     def container(self) -> Tuple[str, int]:
@@ -118,6 +133,39 @@ def write_llama(path: str, hyperparameters: Dict[str, int], tensors: Dict[str, n
         tl = (C.c_uint32 * nv)(*[len(t) for t, _ in vocabulary])
         ts = (C.c_float * nv)(*[s for _, s in vocabulary])
     rc = L.b200_ggml_write_llama(path.encode(), C.byref(hp), n_mult, quantization_version * 1000 + llama_ftype, tb, tl, ts, infos, datas, len(tensors))
+    if rc != 0:
+        raise LoadError(rc, f"write {path}")
+
+
+def write_model(path: str, arch: str, header: Dict[str, int], tensors: Dict[str, np.ndarray], shapes: Dict[str, Tuple[int, ...]], wtype: int,
+                vocabulary: Optional[Sequence[Tuple[bytes, float]]] = None):
+    """ggml::format::save for any of the three architectures: `header` holds the words of HPARAM_NAMES[arch]."""
+    L = _lib.lib()
+    words = [int(header[k]) if k != "n_vocab_again" else int(header["n_vocab"]) for k in HPARAM_NAMES[arch]]
+    infos = (_lib.GgmlTensorInfo * len(tensors))()
+    datas = (C.c_void_p * len(tensors))()
+    keep = []
+    for i, (name, arr) in enumerate(tensors.items()):
+        a = np.ascontiguousarray(arr)
+        keep.append(a)
+        shp = shapes[name]
+        infos[i].name = name.encode()
+        infos[i].type = 0 if a.dtype == np.float32 else wtype
+        infos[i].n_dims = len(shp)
+        infos[i].ne[0] = shp[-1]
+        infos[i].ne[1] = shp[0] if len(shp) == 2 else 1
+        infos[i].nbytes = a.nbytes
+        datas[i] = a.ctypes.data
+    nv = int(header["n_vocab"])
+    tb = tl = ts = None
+    if vocabulary is not None:
+        assert len(vocabulary) == nv
+        bufs = [C.create_string_buffer(t, len(t)) for t, _ in vocabulary]
+        keep.append(bufs)
+        tb = (C.c_void_p * nv)(*[C.cast(b, C.c_void_p) for b in bufs])
+        tl = (C.c_uint32 * nv)(*[len(t) for t, _ in vocabulary])
+        ts = (C.c_float * nv)(*[s for _, s in vocabulary])
+    rc = L.b200_ggml_write(path.encode(), (C.c_int32 * len(words))(*words), len(words), nv, tb, tl, ts, infos, datas, len(tensors))
     if rc != 0:
         raise LoadError(rc, f"write {path}")
 

@@ -127,6 +127,42 @@ def test_legacy_containers_and_quantization_version_rule(orc, tmp_path):
         loader.GgmlFile(p).llama_hyperparameters()
 
 
+def test_gpt2_and_neox_headers(orc, tmp_path):
+    """the other two architectures of the reference: 6 words + n_vocab repeated (gpt2 lib.rs:394-416), 8 words with a 0|1 bool (gptneox lib.rs:431-442)"""
+    from llm_b200 import loader
+    hp, tens = synth.make_gpt2(synth.GPT2_CONFIGS["gpt2-tiny"], B.Q4_0, orc.quantize, lm_head=True)
+    p = str(tmp_path / "gpt2.ggjt")
+    loader.write_model(p, "gpt2", dict(hp, file_type=2002), tens, synth.gpt2_tensor_shapes(hp, lm_head=True), hp["wtype"], vocabulary=_vocab(hp["n_vocab"]))
+    f = loader.GgmlFile(p, "gpt2")
+    h = f.hyperparameters()
+    assert h == dict(n_vocab=hp["n_vocab"], n_ctx=hp["n_ctx"], n_embd=hp["n_embd"], n_head=hp["n_head"], n_layer=hp["n_layer"], file_type=2002, n_vocab_again=hp["n_vocab"])
+    t = f.tensors()
+    assert [x["name"] for x in t] == list(tens.keys()) and all(x["offset"] % 32 == 0 for x in t)
+    wpe = next(i for i, x in enumerate(t) if x["name"] == "model/wpe")
+    assert t[wpe]["type"] == 0 and np.array_equal(f.tensor_bytes(wpe).view(np.float32).reshape(hp["n_ctx"], hp["n_embd"]), tens["model/wpe"])
+    f.close()
+    with pytest.raises(loader.LoadError):                      # read as the wrong architecture: the vocabulary no longer lines up
+        loader.GgmlFile(p, "gptneox")
+    hn, tn = synth.make_neox(synth.NEOX_CONFIGS["neox-tiny"], B.Q5_1, orc.quantize)
+    p2 = str(tmp_path / "neox.ggjt")
+    loader.write_model(p2, "gptneox", dict(hn, file_type=2009), tn, synth.neox_tensor_shapes(hn), hn["wtype"])
+    f = loader.GgmlFile(p2, "gptneox")
+    h = f.hyperparameters()
+    assert h["n_rot"] == hn["n_rot"] and h["use_parallel_residual"] == 1 and h["file_type"] == 2009 and h["n_ctx"] == hn["n_ctx"]
+    assert len(f.tensors()) == len(tn) and len(f.vocabulary()) == hn["n_vocab"]
+    f.close()
+    # gpt2 header whose repeated n_vocab disagrees -> InvariantBroken; neox header whose bool is 2 -> Io (InvalidData)
+    _raw_file(str(tmp_path / "bad1.bin"), hp=(4, 16, 64, 2, 1, 2002, 5))
+    with pytest.raises(loader.LoadError) as e:
+        loader.GgmlFile(str(tmp_path / "bad1.bin"), "gpt2")
+    assert e.value.kind == "InvariantBroken"
+    with open(str(tmp_path / "bad2.bin"), "wb") as fp:
+        fp.write(struct.pack("<II8i", 0x67676a74, 3, 4, 16, 64, 2, 1, 8, 2, 2002))
+    with pytest.raises(loader.LoadError) as e:
+        loader.GgmlFile(str(tmp_path / "bad2.bin"), "gptneox")
+    assert e.value.kind == "Io"
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["q4_0", "q5_1", "q8_0"])
 def test_model_loaded_from_file_is_bit_exact(orc, tmp_path, name):
