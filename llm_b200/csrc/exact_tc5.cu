@@ -1,0 +1,318 @@
+// llm_b200/csrc/exact_tc5.cu -- bit-exact ggml_mul_mat for a batch of activation rows (prefill) on Blackwell's 5th-generation tensor cores:
+// TMA-staged activations, tcgen05.mma into TMEM, tcgen05.ld epilogue, warp-specialised, one CTA per SM.
+//
+// What has to come out (AVX2 build of ggml_vec_dot_q*_q8_*, LC/ggml.c:2434-2457, 2561-2590, 2700-2737, 2841-2879, 2953-2977; driver :10526-10572):
+// per output (token t, row n) eight f32 lane accumulators; for every 32-element block b IN ORDER
+//     acc_L = fma(d_w[n,b] * d_x[t,b], (float)S_L, acc_L),   S_L = sum_{e<4} w[4L+e] * x[4L+e]   (integers)
+// then ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))  (+ summs = fma chain of m_w * s_x for Q4_1 / Q5_1).
+//
+// The eight S_L of a (token, row, block) are produced by the tensor core with a BLOCK-DIAGONAL B operand (same idea as exact_mma.cu, now in
+// tcgen05 form): for one half-block (16 elements = one kind::f16 K step)
+//     A = 128 tokens x 16 elements (the Q8 quants as f16, exact)            -- M = 128  = TMEM lanes
+//     B = (32 rows x 4 lanes) x 16 elements, column (n, l) non-zero only at elements 4l..4l+3 (the integer weights as f16, exact)   -- N = 128
+//     D[t][(n, l)] = S_{4h+l}  exactly (|S| < 2^17; accumulate is OFF: every MMA is a fresh product)
+// Two MMAs (halves h = 0, 1) per block fill 256 TMEM columns = all eight partial dots of 128 tokens x 32 rows; TMEM holds two such blocks
+// (512 columns) so the tensor core runs one block ahead of the epilogue.  What stays on the CUDA cores is precisely the reference's rounding
+// sequence: one f32 product and eight ordered fmas per (token, row, block) = the bound of this kernel (fp32 pipe), see DESIGN.md section 4.
+//
+// Warp roles (384 threads):  warp 0   : TMA producer  -- cp.async.bulk.tensor of the f16 activations [128 tokens x 64 elements], 128B swizzle
+//                            warp 1   : MMA issuer    -- one thread: tcgen05.mma x 4 per stage, tcgen05.commit to the stage / TMEM barriers
+//                            warps 2-3: expanders     -- packed weights (L2) -> block-diagonal f16 B operands in shared memory + f32 scales
+//                            warps 4-11: epilogue     -- tcgen05.ld, the ordered fp32 chains (packed fma.rn.f32x2), final hsum, store
+// A thread of the epilogue IS a token (TMEM lane): it owns 16 rows x 8 lanes of accumulators; d_x is its private scalar, d_w is warp-uniform.
+#include <string.h>
+
+#include "kernels.cuh"
+#include "tc5.cuh"
+
+namespace b200 {
+
+namespace {
+
+using namespace tc5;
+
+constexpr int TM = 128, TN = 32, NST = 4, DWR = 2 * NST + 4;     // tokens / rows per CTA, pipeline stages (2 blocks each), scale ring (blocks)
+constexpr int A_STAGE = TM * 64 * 2;                              // 16 KB: [128 tokens][64 elements] f16, 128-byte rows, swizzled
+constexpr int B_HALF = 128 * 16 * 2;                              // 4 KB: one block-diagonal operand (N = 128 columns x K = 16), no swizzle
+constexpr int B_STAGE = 4 * B_HALF;                               // [block j][half h]
+constexpr int B_LBO = 128, B_SBO = 256;                           // K-adjacent core matrices contiguous, 8-column groups 256 B apart
+constexpr int NTHREADS = 384;
+constexpr int SMEM_BYTES = 1024 + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + 256;
+
+template <int TYPE> struct Tc {
+    static constexpr bool MIN = (TYPE == T_Q4_1 || TYPE == T_Q5_1), QH = (TYPE == T_Q5_0 || TYPE == T_Q5_1), Q8 = (TYPE == T_Q8_0);
+    static constexpr int QS = Q8 ? 32 : 16, DM = MIN ? 4 : 2;
+    static constexpr uint32_t OFF = TYPE == T_Q4_0 ? 0x64086408u : TYPE == T_Q5_0 ? 0x64106410u : TYPE == T_Q8_0 ? 0x64806480u : 0x64006400u;
+};
+
+// bytes (sel picks two of the four bytes of v) -> half2(1024 + lo, 1024 + hi) - off   (exact: the fp16 magic-number trick)
+__device__ __forceinline__ uint32_t bytes_to_half2(uint32_t v, uint32_t sel, uint32_t off_h2) {
+    const uint32_t p = __byte_perm(v, 0x64646464u, sel);
+    __half2 a, o;
+    memcpy(&a, &p, 4); memcpy(&o, &off_h2, 4);
+    const __half2 h = __hsub2(a, o);
+    uint32_t r; memcpy(&r, &h, 4);
+    return r;
+}
+
+struct WRaw { uint4 q; uint32_t dm; uint32_t qh; };               // one (row, block) as fetched by an expander thread
+
+template <int TYPE>
+__global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, const QWeight w, const float2 *__restrict__ xds,
+                                                                   float *__restrict__ dst, int64_t ldd, int64_t B, const float *__restrict__ addend, int64_t lda) {
+    using T = Tc<TYPE>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;                     // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t *const sptr = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t sA = sbase, sB = sbase + NST * A_STAGE, sW = sB + NST * B_STAGE, sBar = sW + DWR * TN * 8;
+    uint8_t *const pB = sptr + NST * A_STAGE;
+    float2 *const pW = (float2 *)(sptr + NST * (A_STAGE + B_STAGE));
+    uint32_t *const pTmem = (uint32_t *)(sptr + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + 128);
+    auto bar_a_full = [&](int s) { return sBar + 8 * s; };
+    auto bar_b_full = [&](int s) { return sBar + 8 * (NST + s); };
+    auto bar_empty = [&](int s) { return sBar + 8 * (2 * NST + s); };
+    auto bar_t_full = [&](int i) { return sBar + 8 * (3 * NST + i); };
+    auto bar_t_empty = [&](int i) { return sBar + 8 * (3 * NST + 2 + i); };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_base = (int64_t)blockIdx.x * TN, m_base = (int64_t)blockIdx.y * TM;
+    const int nb = (int)w.nb, nstage = nb / 2;
+
+    // ---- set-up: zero the operand buffers (the off-diagonal zeros are written once), barriers, TMEM ----
+    for (int i = tid; i < NST * B_STAGE / 16; i += NTHREADS) ((uint4 *)pB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < NST; s++) { mbar_init(bar_a_full(s), 1); mbar_init(bar_b_full(s), 64); mbar_init(bar_empty(s), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar_t_full(i), 1); mbar_init(bar_t_empty(i), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(smem_u32(pTmem), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *pTmem;
+    bool dead = false;
+
+    if (warp < 4) {
+        reg_dealloc<72>();
+        if (warp == 0) {
+            // ================= TMA producer =================
+            if (lane == 0) {
+                for (int st = 0; st < nstage; st++) {
+                    const int slot = st % NST; const uint32_t par = (st / NST) & 1;
+                    mbar_wait(bar_empty(slot), par ^ 1, dead);
+                    mbar_expect_tx(bar_a_full(slot), A_STAGE);
+                    tma_load_2d(sA + slot * A_STAGE, &tmap_x, st * 64, (int)m_base, bar_a_full(slot));
+                }
+            }
+        } else if (warp == 1) {
+            // ================= MMA issuer =================
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc_f16(128, 128);
+                for (int st = 0; st < nstage; st++) {
+                    const int slot = st % NST; const uint32_t par = (st / NST) & 1;
+                    mbar_wait(bar_a_full(slot), par, dead);
+                    mbar_wait(bar_b_full(slot), par, dead);
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int blk = 2 * st + j, buf = blk & 1;
+                        mbar_wait(bar_t_empty(buf), ((blk >> 1) & 1) ^ 1, dead);
+                        tc_fence_after();
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const uint64_t ad = make_smem_desc(sA + slot * A_STAGE + j * 64 + h * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t bd = make_smem_desc(sB + slot * B_STAGE + (j * 2 + h) * B_HALF, B_LBO, B_SBO, LAYOUT_NONE);
+                            mma_f16_ss(tmem + buf * 256 + h * 128, ad, bd, idesc, 0u);
+                        }
+                        tc_commit(bar_t_full(buf));
+                    }
+                    tc_commit(bar_empty(slot));
+                }
+            }
+        } else {
+            // ================= expanders: thread (row r, half h) =================
+            const int et = tid - 64, r = et >> 1, h = et & 1;
+            const int64_t n = n_base + r < w.N ? n_base + r : w.N - 1;
+            const uint8_t *q_ptr = w.qs + (size_t)n * nb * T::QS + (T::Q8 ? 16 * h : 0);
+            const uint8_t *d_ptr = (const uint8_t *)w.dm + (size_t)n * nb * T::DM;
+            const uint32_t *h_ptr = T::QH ? w.qh + (size_t)n * nb : nullptr;
+            auto fetch = [&](int blk) {
+                WRaw x;
+                x.q = *(const uint4 *)(q_ptr + (size_t)blk * T::QS);
+                x.dm = T::MIN ? *(const uint32_t *)(d_ptr + (size_t)blk * 4) : (uint32_t)*(const uint16_t *)(d_ptr + (size_t)blk * 2);
+                x.qh = T::QH ? h_ptr[blk] : 0u;
+                return x;
+            };
+            // column (r, l) of half h: non-zero K slots 4l..4l+3  ->  8 bytes at this offset inside the 4 KB operand
+            uint32_t col_off[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++) col_off[l] = (uint32_t)((r >> 1) * B_SBO + (l >> 1) * B_LBO + (4 * (r & 1) + l) * 16 + (l & 1) * 8);
+            auto expand = [&](const WRaw &x, int slot, int j, int blk) {
+                uint8_t *out = pB + slot * B_STAGE + (j * 2 + h) * B_HALF;
+                const uint32_t qw[4] = {x.q.x, x.q.y, x.q.z, x.q.w};
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    uint32_t v;
+                    if (T::Q8) v = qw[l] ^ 0x80808080u;                                           // int8 -> biased 0..255
+                    else {
+                        v = (qw[l] >> (4 * h)) & 0x0F0F0F0Fu;                                      // elements 16h + 4l .. +3
+                        if (T::QH) v |= spread4_to_bit4((x.qh >> (16 * h + 4 * l)) & 0xFu);
+                    }
+                    uint2 f;
+                    f.x = bytes_to_half2(v, 0x4140u, T::OFF);
+                    f.y = bytes_to_half2(v, 0x4342u, T::OFF);
+                    *(uint2 *)(out + col_off[l]) = f;
+                }
+                if (h == 0) {
+                    float2 dm;
+                    if (T::MIN) { __half2 hh; memcpy(&hh, &x.dm, 4); dm = make_float2(__low2float(hh), __high2float(hh)); }
+                    else dm = make_float2(__half2float(__ushort_as_half((unsigned short)x.dm)), 0.f);
+                    pW[(blk % DWR) * TN + r] = dm;
+                }
+            };
+            WRaw c0[2], c1[2];                                                                     // two stages in flight
+            if (nstage > 0) { c0[0] = fetch(0); c0[1] = fetch(1); }
+            if (nstage > 1) { c1[0] = fetch(2); c1[1] = fetch(3); }
+            for (int st = 0; st < nstage; st += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int s2 = st + u;
+                    if (s2 >= nstage) break;
+                    const int slot = s2 % NST; const uint32_t par = (s2 / NST) & 1;
+                    mbar_wait(bar_empty(slot), par ^ 1, dead);
+                    WRaw *cur = u ? c1 : c0;
+                    expand(cur[0], slot, 0, 2 * s2); expand(cur[1], slot, 1, 2 * s2 + 1);
+                    if (s2 + 2 < nstage) { cur[0] = fetch(2 * (s2 + 2)); cur[1] = fetch(2 * (s2 + 2) + 1); }
+                    fence_proxy_async_smem();
+                    mbar_arrive(bar_b_full(slot));
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: thread = token (TMEM lane), 16 rows x 8 lanes =================
+        reg_alloc<216>();
+        const int q = warp & 3, ch = (warp - 4) >> 2;
+        const int64_t m = m_base + q * 32 + lane;
+        const float2 *xp = xds + (size_t)(m < B ? m : B - 1) * nb;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ch * 64;
+        float2 acc[16][4];
+        float summs[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) { summs[r] = 0.f;
+#pragma unroll
+            for (int p = 0; p < 4; p++) acc[r][p] = make_float2(0.f, 0.f); }
+
+        float4 xd = *(const float4 *)xp;                                                           // {d, aux} of blocks 0, 1 (nb is even: 16-byte aligned)
+        for (int st = 0; st < nstage; st++) {
+            float4 xd_next = xd;
+            if (st + 1 < nstage) xd_next = *(const float4 *)(xp + 2 * (st + 1));
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int blk = 2 * st + j, buf = blk & 1;
+                const float dx = j ? xd.z : xd.x, sx = j ? xd.w : xd.y;
+                const float2 *wrow = pW + (blk % DWR) * TN + ch * 16;
+                mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {                                                      // 4 rows per chunk
+                    uint32_t d0[16], d1[16];
+                    tmem_ld_x16(t_lane + buf * 256 + c * 16, d0);                                  // lanes 0-3 of rows 4c..4c+3
+                    tmem_ld_x16(t_lane + buf * 256 + 128 + c * 16, d1);                            // lanes 4-7
+                    tc_wait_ld();
+                    if (c == 3) {                                                                  // every column of this buffer has been read
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_t_empty(buf));
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++) {
+                        const int r = c * 4 + rr;
+                        const float2 dm = wrow[r];
+                        const float s = __fmul_rn(dm.x, dx);
+                        const float2 s2 = make_float2(s, s);
+                        acc[r][0] = ffma2(s2, make_float2(__uint_as_float(d0[rr * 4 + 0]), __uint_as_float(d0[rr * 4 + 1])), acc[r][0]);
+                        acc[r][1] = ffma2(s2, make_float2(__uint_as_float(d0[rr * 4 + 2]), __uint_as_float(d0[rr * 4 + 3])), acc[r][1]);
+                        acc[r][2] = ffma2(s2, make_float2(__uint_as_float(d1[rr * 4 + 0]), __uint_as_float(d1[rr * 4 + 1])), acc[r][2]);
+                        acc[r][3] = ffma2(s2, make_float2(__uint_as_float(d1[rr * 4 + 2]), __uint_as_float(d1[rr * 4 + 3])), acc[r][3]);
+                        if (T::MIN) summs[r] = __fmaf_rn(dm.y, sx, summs[r]);
+                    }
+                }
+            }
+            xd = xd_next;
+        }
+        // hsum_float_8 (LC/ggml.c:608-616): ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), then + summs
+        if (m < B) {
+            float *out = dst + (size_t)m * ldd + n_base + ch * 16;
+            const float *add = addend ? addend + (size_t)m * lda + n_base + ch * 16 : nullptr;
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float a0 = acc[r][0].x, a1 = acc[r][0].y, a2 = acc[r][1].x, a3 = acc[r][1].y;
+                const float a4 = acc[r][2].x, a5 = acc[r][2].y, a6 = acc[r][3].x, a7 = acc[r][3].y;
+                float v = __fadd_rn(__fadd_rn(__fadd_rn(a0, a4), __fadd_rn(a2, a6)), __fadd_rn(__fadd_rn(a1, a5), __fadd_rn(a3, a7)));
+                if (T::MIN) v = __fadd_rn(v, summs[r]);
+                if (n_base + ch * 16 + r < w.N) out[r] = add ? __fadd_rn(v, add[r]) : v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// quantize_act with the quants written as fp16 in plain row-major [B][K] (the TMA source), same arithmetic as quantize_act_kernel (quant.cu)
+template <bool Q81>
+__global__ void __launch_bounds__(256) quantize_act_f16_rm_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__ xh, float2 *__restrict__ ds,
+                                                                  int64_t nbk, int64_t total_blocks) {
+    const int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blk >= total_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blk / nbk, b = blk - row * nbk;
+    const float v = x[row * ldx + b * QK + lane];
+    const float amax = warp_max(fabsf(v));
+    const float d = __fdiv_rn(amax, 127.f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+    const int q = __float2int_rn(__fmul_rn(v, id));
+    const int isum = warp_sum(q);
+    xh[(row * nbk + b) * QK + lane] = __int2half_rn(q);
+    if (lane == 0) ds[blk] = Q81 ? make_float2(d, __fmul_rn(d, (float)isum)) : make_float2(__half2float(__float2half_rn(d)), (float)isum);
+}
+
+template <int TYPE>
+void launch_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st) {
+    static bool set = false;                                        // per-process attribute (one device per process: include/llm_b200.h)
+    if (!set) { B200_CHECK(cudaFuncSetAttribute(mm_exact_tc5_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); set = true; }
+    const CUtensorMap tm = make_tmap_2d_f16_sw128(xh, (uint64_t)w.K, (uint64_t)B, (uint64_t)w.K * 2, TM);
+    dim3 grid((unsigned)((w.N + TN - 1) / TN), (unsigned)((B + TM - 1) / TM));
+    mm_exact_tc5_kernel<TYPE><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, w, xds, dst, ldd, B, addend, lda);
+    B200_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void quantize_act_f16_rm(int vdt, const float *x, int64_t ldx, __half *xh, float2 *ds, int64_t K, int64_t B, cudaStream_t st) {
+    const int64_t nbk = K / QK, total = nbk * B;
+    if (total == 0) return;
+    if (vdt == T_Q8_1) quantize_act_f16_rm_kernel<true><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total);
+    else               quantize_act_f16_rm_kernel<false><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total);
+    B200_CHECK(cudaGetLastError());
+}
+
+int exact_tc5_check_timeout() { return tc5::check_timeout("mm_exact_tc5_kernel"); }
+
+// xh = quantized activations as fp16, row-major [B][K] (quantize_act_f16_rm); xds = {d, aux} per (token, block)
+void mul_mat_q_exact_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st) {
+    if (w.N == 0 || B == 0) return;
+    B200_ASSERT(w.nb % 2 == 0 && ((uintptr_t)xh & 15) == 0);
+    switch (w.type) {
+        case T_Q4_0: launch_tc5<T_Q4_0>(w, xh, xds, dst, ldd, B, addend, lda, st); break;
+        case T_Q4_1: launch_tc5<T_Q4_1>(w, xh, xds, dst, ldd, B, addend, lda, st); break;
+        case T_Q5_0: launch_tc5<T_Q5_0>(w, xh, xds, dst, ldd, B, addend, lda, st); break;
+        case T_Q5_1: launch_tc5<T_Q5_1>(w, xh, xds, dst, ldd, B, addend, lda, st); break;
+        case T_Q8_0: launch_tc5<T_Q8_0>(w, xh, xds, dst, ldd, B, addend, lda, st); break;
+        default: B200_ASSERT(!"mul_mat_q_exact_tc5: unsupported weight type");
+    }
+}
+
+}  // namespace b200

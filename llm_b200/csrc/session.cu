@@ -722,6 +722,12 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
         __half *xh = (__half *)R.op_arena.get((size_t)xh_bytes(K, B), st);
         quantize_act_f16(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
         mul_mat_q_exact_mma(w, xh, xds, dd, N, B, nullptr, 0, st);
+    } else if (impl == B200_MM_EXACT_TC5) {
+        __half *xh = (__half *)R.op_arena.get((size_t)B * K * 2 + 16, st);
+        quantize_act_f16_rm(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
+        mul_mat_q_exact_tc5(w, xh, xds, dd, N, B, nullptr, 0, st);
+        B200_CHECK(cudaStreamSynchronize(st));
+        if (exact_tc5_check_timeout() != 0) return B200_ERR_IO;
     } else if (impl == B200_MM_EXACT_STREAM) {
         if (!mmv_exact_stream_supported(w)) return B200_ERR_BAD_ARG;
         int4 *pack = (int4 *)R.op_arena.get((size_t)(K / QK) * 64, st);
@@ -732,6 +738,46 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
     else mul_mat_q(w, xq, xds, dd, N, B, nullptr, 0, st);
     B200_CHECK(cudaMemcpyAsync(dst, dd, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
     B200_CHECK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// Kernel-only timing of one weight mat-mul on device-resident synthetic operands (seeded random weights and activations): used by
+// tools/prefill_gemm_bench.py and bench.py's prefill roofline; impl = B200_MM_EXACT_MMA / B200_MM_EXACT_TC5 / B200_MM_TENSOR
+int b200_op_bench_mul_mat(int32_t wtype, int64_t K, int64_t N, int64_t B, int32_t impl, int32_t iters, float *ms_out) {
+    if (!is_quant(wtype) || K % 64 || !ms_out || iters < 1) return B200_ERR_BAD_ARG;
+    Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
+    cudaStream_t st = R.stream;
+    QWeight w;
+    const size_t pb = qweight_layout(w, wtype, K, N, nullptr);
+    void *base = R.op_arena.get(pb, st);
+    qweight_layout(w, wtype, K, N, base);
+    synth_qweight(w, 777u, st);
+    float *dx = (float *)R.op_arena.get((size_t)B * K * 4, st);
+    float *dd = (float *)R.op_arena.get((size_t)B * N * 4, st);
+    float2 *xds = (float2 *)R.op_arena.get((size_t)B * (K / QK) * sizeof(float2), st);
+    __half *xh = (__half *)R.op_arena.get(xh_bytes(K, B) + 16, st);
+    int8_t *xq = (int8_t *)R.op_arena.get((size_t)B * K, st);
+    synth_gain(dx, B * K, 12345u, st);
+    if (impl == B200_MM_EXACT_TC5) quantize_act_f16_rm(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
+    else if (impl == B200_MM_EXACT_MMA) quantize_act_f16(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
+    else quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
+    auto run = [&]() {
+        if (impl == B200_MM_EXACT_TC5) mul_mat_q_exact_tc5(w, xh, xds, dd, N, B, nullptr, 0, st);
+        else if (impl == B200_MM_EXACT_MMA) mul_mat_q_exact_mma(w, xh, xds, dd, N, B, nullptr, 0, st);
+        else mul_mat_q(w, xq, xds, dd, N, B, nullptr, 0, st);
+    };
+    for (int i = 0; i < 2; i++) run();
+    cudaEvent_t e0, e1;
+    B200_CHECK(cudaEventCreate(&e0)); B200_CHECK(cudaEventCreate(&e1));
+    B200_CHECK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; i++) run();
+    B200_CHECK(cudaEventRecord(e1, st));
+    B200_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    B200_CHECK(cudaEventDestroy(e0)); B200_CHECK(cudaEventDestroy(e1));
+    if (impl == B200_MM_EXACT_TC5 && exact_tc5_check_timeout() != 0) return B200_ERR_IO;
     return B200_OK;
 }
 

@@ -1,0 +1,150 @@
+// llm_b200/csrc/tc5.cuh -- thin inline-PTX wrappers of the Blackwell (sm_100a) machinery used by the tcgen05 GEMMs:
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05.mma / .commit / .ld, TMEM allocation, setmaxnreg, packed f32x2 arithmetic.
+// Descriptor bit layouts follow the PTX ISA 8.6 "tcgen05 matrix / instruction descriptor" tables.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200 {
+namespace tc5 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Spin with a watchdog: a protocol bug must not hang the GPU box (a hang is a strike).  After ~1 s without progress the thread records
+// (bar, parity, block, thread) in g_timeout, turns "dead" (all its later waits return at once) and the kernel runs to completion with
+// garbage results; the host reads g_timeout (tc5_check_timeout) in the op-level entry points and the tests.
+__device__ unsigned int g_timeout[8];
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool &dead) {
+    if (dead || mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) {
+            dead = true;
+            if (atomicAdd(&g_timeout[0], 1u) == 0u) { g_timeout[1] = bar; g_timeout[2] = parity; g_timeout[3] = blockIdx.x; g_timeout[4] = blockIdx.y; g_timeout[5] = threadIdx.x; }
+            return;
+        }
+    }
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMA ----------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) { asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *m, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- TMEM / tcgen05 -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory"); }
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// all previously issued tcgen05.mma of this thread complete -> one arrival on `bar` (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], f16/bf16 inputs, f32 accumulate; issued by ONE thread
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor (K-major operands).  Canonical layouts in 16-byte units (cute/atom/mma_traits_sm100.hpp):
+//   no swizzle : ((8,n),2):((1,SBO),LBO)   -- 8 rows x 16 B core matrices; LBO = stride between the two K halves, SBO = between 8-row groups
+//   128B swizzle: ((8,n),2):((8,SBO),1)    -- rows of 128 B, 16-byte chunk c of row r at chunk (c ^ (r & 7)); SBO = 1024 B; LBO unused
+constexpr uint64_t LAYOUT_NONE = 0, LAYOUT_SW128 = 2;
+__host__ __device__ inline uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46) /* descriptor version (Blackwell) */ | (layout << 61);
+}
+// Instruction descriptor, kind::f16: D f32, A/B f16 (bf16 = 1), both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_format = 0) {
+    return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// 32 lanes x 32 bit, x32 columns: thread i of warp w reads TMEM lane 32*(w%4)+i, columns [col, col+32)
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+                 "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                   "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// Blackwell packed fp32: two IEEE round-to-nearest fmas / muls per instruction (per-lane results identical to fmaf / fmul)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\tfma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart statically and not libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// returns 0 if no mbarrier wait of this translation unit's kernels ever timed out; prints the first record otherwise
+inline int check_timeout(const char *what) {
+    unsigned int h[8] = {0};
+    if (cudaMemcpyFromSymbol(h, g_timeout, sizeof(h)) != cudaSuccess) return -1;
+    if (h[0] == 0) return 0;
+    fprintf(stderr, "llm_b200: %s: %u mbarrier waits timed out; first: bar +%u parity %u block (%u,%u) thread %u\n", what, h[0], h[1], h[2], h[3], h[4], h[5]);
+    return 1;
+}
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+            fprintf(stderr, "llm_b200: cuTensorMapEncodeTiled is not available\n");
+            exit(1);
+        }
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// 2-D f16/bf16 row-major [rows][cols] tensor, box [box_rows][64 columns = 128 B], 128-byte swizzle, out-of-bounds rows read as zero
+inline CUtensorMap make_tmap_2d_f16_sw128(const void *base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_rows, bool bf16 = false) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {64, box_rows}, estr[2] = {1, 1};
+    CUresult r = encode_tiled_fn()(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "llm_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); exit(1); }
+    return m;
+}
+
+}  // namespace tc5
+}  // namespace b200

@@ -92,6 +92,23 @@ def test_mul_mat_tensor_core_bit_exact(L, orc, name, t, K, N, Bn):
 
 
 @pytest.mark.parametrize("name,t", TYPES)
+@pytest.mark.parametrize("K,N,Bn", [(4096, 200, 128), (256, 33, 16), (704, 100, 40), (11008, 48, 37), (4096, 17, 300), (64, 16, 129), (2048, 130, 512),
+                                     (5120, 96, 257), (128, 32, 1)])
+def test_mul_mat_tcgen05_bit_exact(L, orc, name, t, K, N, Bn):
+    """prefill GEMM on the 5th-generation tensor cores (TMA-staged activations, block-diagonal tcgen05.mma into TMEM, tcgen05.ld epilogue;
+    exact_tc5.cu): same bits as ggml_compute_forward_mul_mat, for every format, ragged N / token counts and K tails of the stage ring"""
+    rng = np.random.default_rng(K * 13 + N + t)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    x = (rng.standard_normal((Bn, K)) * rng.uniform(0.05, 8, (Bn, 1))).astype(np.float32)
+    x[Bn // 2, :32] = 0.0
+    wq = orc.quantize(t, w)
+    want = orc.mul_mat(t, wq, x)
+    got = np.empty((Bn, N), np.float32)
+    assert L.b200_op_mul_mat(t, wq.ctypes.data, K, N, x.ctypes.data, Bn, got.ctypes.data, 7) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, K, N, Bn, rel(got, want), int((got != want).sum()))
+
+
+@pytest.mark.parametrize("name,t", TYPES)
 @pytest.mark.parametrize("K,N,Bn", [(4096, 200, 1), (11008, 96, 2), (256, 33, 3), (5120, 1000, 1), (4096, 31, 1), (2048, 32, 1), (13824, 64, 1)])
 def test_mul_mat_stream_bit_exact(L, orc, name, t, K, N, Bn):
     """decode mat-vec fed by TMA bulk copies (exact_stream.cu): same bits as the reference, any tile/chunk tail"""
