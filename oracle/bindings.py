@@ -197,6 +197,19 @@ class RefLlama:
     def reset(self):
         self.ref.lib.rh_llama_reset(self.m)
 
+    def set_n_past(self, n):
+        self.ref.lib.rh_llama_set_n_past(self.m, int(n))
+
+    def set_rope(self, freq_base, freq_scale):
+        self.ref.lib.rh_llama_set_rope.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        self.ref.lib.rh_llama_set_rope(self.m, freq_base, freq_scale)
+
+    def kv_ptr(self, which):
+        """(address, nbytes) of the f16 K (0) / V (1) cache: lets a caller install cache contents (bench.py's CPU arm)"""
+        nb = C.c_size_t(0)
+        p = self.ref.lib.rh_llama_kv(self.m, which, C.byref(nb))
+        return p, nb.value
+
     def eval(self, tokens):
         tokens = np.ascontiguousarray(tokens, np.int32)
         logits = np.empty((tokens.size, self.hp["n_vocab"]), np.float32)
@@ -367,6 +380,14 @@ class OracleLlama:
 
     def reset(self):
         self.orc.lib.or_llama_reset(self.m)
+
+    def set_n_past(self, n):
+        self.orc.lib.or_llama_set_n_past.argtypes = [C.c_void_p, C.c_int]
+        self.orc.lib.or_llama_set_n_past(self.m, int(n))
+
+    def set_rope(self, freq_base, freq_scale):
+        self.orc.lib.or_llama_set_rope.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        self.orc.lib.or_llama_set_rope(self.m, freq_base, freq_scale)
 
     def eval(self, tokens, tap_layer=None):
         tokens = np.ascontiguousarray(tokens, np.int32)

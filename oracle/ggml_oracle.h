@@ -71,6 +71,8 @@ or_llama *or_llama_new(const or_hparams *hp);
 /* returns the host buffer the named tensor lives in (loader names, crates/models/llama/src/lib.rs:52-91) */
 void *or_llama_tensor(or_llama *m, const char *name, size_t *nbytes);
 void  or_llama_reset(or_llama *m);
+void  or_llama_set_n_past(or_llama *m, int n);
+void  or_llama_set_rope(or_llama *m, float freq_base, float freq_scale);
 int   or_llama_eval(or_llama *m, const int32_t *tokens, int n, float *logits_all);
 void *or_llama_kv(or_llama *m, int which, size_t *nbytes);
 void  or_llama_free(or_llama *m);

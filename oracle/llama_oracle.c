@@ -23,13 +23,14 @@ struct or_llama {
     uint16_t *memory_k, *memory_v;
     int n_past;
     float *tap; int tap_layer, tap_stage;
+    float rope_base, rope_scale;
 };
 
 static void *xmalloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "oracle: out of memory (%zu)\n", n); abort(); } return p; }
 
 or_llama *or_llama_new(const or_hparams *hp) {
     or_llama *m = calloc(1, sizeof(*m));
-    m->hp = *hp; m->tap_layer = -2; m->tap_stage = 11;
+    m->hp = *hp; m->tap_layer = -2; m->tap_stage = 11; m->rope_base = 10000.0f; m->rope_scale = 1.0f;
     const int e = hp->n_embd, f = hp->n_ff, v = hp->n_vocab, t = hp->wtype;
     const int gqa = e / (hp->n_head / hp->n_head_kv);
     m->wte = xmalloc(or_row_bytes(t, e) * v);
@@ -74,6 +75,8 @@ void *or_llama_tensor(or_llama *m, const char *name, size_t *nbytes) {
 }
 
 void or_llama_reset(or_llama *m) { m->n_past = 0; }
+void or_llama_set_n_past(or_llama *m, int n) { m->n_past = n; }
+void or_llama_set_rope(or_llama *m, float freq_base, float freq_scale) { m->rope_base = freq_base; m->rope_scale = freq_scale; }
 void or_llama_set_tap(or_llama *m, float *buf, int il) { m->tap = buf; m->tap_layer = il; m->tap_stage = 11; }
 /* stage taps inside layer il (debugging GPU parity): 1 cur after attn rms_norm*gain, 2 q|k|v before rope (q then k then v, each [N][.]),
  * 3 q|k after rope, 4 KQ raw, 5 KQ after scale+mask+softmax, 6 merged KQV, 7 inpFF, 8 cur after ffn norm, 9 w1x|w3x, 10 silu*mul, 11 layer out */
@@ -116,8 +119,8 @@ int or_llama_eval(or_llama *m, const int32_t *tokens, int N, float *logits_all) 
         or_mul_mat(t, L->wk, cur, k, e, gqa, N);                                            /* :208 */
         or_mul_mat(t, L->wv, cur, v, e, gqa, N);                                            /* :223 */
         if (m->tap && m->tap_layer == il && m->tap_stage == 2) { memcpy(m->tap, q, (size_t)N*e*4); memcpy(m->tap + (size_t)N*e, k, (size_t)N*gqa*4); memcpy(m->tap + (size_t)N*(e+gqa), v, (size_t)N*gqa*4); }
-        or_rope(q, hd, n_head, N, n_past, hp->n_rot, 0, 10000.0f, 1.0f);                    /* :190-203 */
-        or_rope(k, hd, n_head_kv, N, n_past, hp->n_rot, 0, 10000.0f, 1.0f);                 /* :204-217 */
+        or_rope(q, hd, n_head, N, n_past, hp->n_rot, 0, m->rope_base, m->rope_scale);                    /* :190-203 */
+        or_rope(k, hd, n_head_kv, N, n_past, hp->n_rot, 0, m->rope_base, m->rope_scale);                 /* :204-217 */
         TAP2(3, q, (size_t)N * e, k, (size_t)N * gqa);
         for (int i = 0; i < N; i++)                                                         /* cpy f32->f16, :243-244 */
             for (int c = 0; c < gqa; c++) {

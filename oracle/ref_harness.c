@@ -52,6 +52,7 @@ typedef struct {
     int n_past;
     int can_offload;
     int finalized;
+    int rope_custom; float rope_base, rope_scale;   /* ModelParameters::rope_overrides (model/mod.rs:197-229) */
 } rh_model;
 
 static size_t rh_tensor_bytes(enum ggml_type t, int64_t ne0, int64_t ne1) {
@@ -201,6 +202,10 @@ int rh_llama_finalize(rh_model *m) {
 }
 
 void rh_llama_reset(rh_model *m) { m->n_past = 0; }
+/* session rewind / restore: continue from position n with whatever the KV cache holds (the bench's CPU arm installs the cache contents) */
+void rh_llama_set_n_past(rh_model *m, int n) { m->n_past = n; }
+/* RoPEOverrides -> op_rope_inplace takes the ggml_rope_custom_inplace branch (crates/ggml/src/context.rs:558-590) */
+void rh_llama_set_rope(rh_model *m, float freq_base, float freq_scale) { m->rope_custom = 1; m->rope_base = freq_base; m->rope_scale = freq_scale; }
 int  rh_llama_n_past(rh_model *m) { return m->n_past; }
 
 /* One forward pass = InferenceSession::compute(Llama::evaluate builder). Writes all n rows of logits
@@ -231,12 +236,12 @@ int rh_llama_eval(rh_model *m, const int32_t *tokens, int n, float *logits_out, 
         rh_use_scratch(m, 0);
         cur = W(m, ggml_rms_norm(ctx0, inpL, 5e-6f));                          /* :183, eps crates/ggml/src/lib.rs:132 */
         cur = W(m, ggml_mul(ctx0, cur, L->attention_norm));                    /* :186 */
-        struct ggml_tensor *Qcur = W(m, ggml_rope_inplace(ctx0,
-            W(m, ggml_reshape_3d(ctx0, W(m, ggml_mul_mat(ctx0, L->wq, cur)), n_embd / n_head, n_head, input_len)),
-            session_len, n_rot, 0, 0));                                        /* :190-203 */
-        struct ggml_tensor *Kcur = W(m, ggml_rope_inplace(ctx0,
-            W(m, ggml_reshape_3d(ctx0, W(m, ggml_mul_mat(ctx0, L->wk, cur)), n_embd / n_head, n_head_kv, input_len)),
-            session_len, n_rot, 0, 0));                                        /* :204-217 */
+        struct ggml_tensor *q3 = W(m, ggml_reshape_3d(ctx0, W(m, ggml_mul_mat(ctx0, L->wq, cur)), n_embd / n_head, n_head, input_len));
+        struct ggml_tensor *k3 = W(m, ggml_reshape_3d(ctx0, W(m, ggml_mul_mat(ctx0, L->wk, cur)), n_embd / n_head, n_head_kv, input_len));
+        struct ggml_tensor *Qcur = W(m, m->rope_custom ? ggml_rope_custom_inplace(ctx0, q3, session_len, n_rot, 0, 1, m->rope_base, m->rope_scale)
+                                                       : ggml_rope_inplace(ctx0, q3, session_len, n_rot, 0, 0));       /* :190-203 */
+        struct ggml_tensor *Kcur = W(m, m->rope_custom ? ggml_rope_custom_inplace(ctx0, k3, session_len, n_rot, 0, 1, m->rope_base, m->rope_scale)
+                                                       : ggml_rope_inplace(ctx0, k3, session_len, n_rot, 0, 0));       /* :204-217 */
         struct ggml_tensor *Vcur = W(m, ggml_transpose(ctx0,
             W(m, ggml_reshape_2d(ctx0, W(m, ggml_mul_mat(ctx0, L->wv, cur)), n_embd_gqa, input_len))));   /* :221-225 */
         struct ggml_tensor *k = W(m, ggml_view_1d(ctx0, m->memory_k, (int64_t)input_len * n_embd_gqa,

@@ -230,3 +230,104 @@ def test_last_row_only_lm_head_and_top_k(orc):
     ids, vals = s.top_k(8)
     assert np.array_equal(ids, np.lexsort((np.arange(ref1.size), -ref1.astype(np.float64)))[:8].astype(np.int32))
     s.close(); m.close()
+
+
+# ---- parity AT the configuration bench.py publishes (VERDICT r01 "next" #1) ---------------------------------------------------------------
+
+def _device_synth_model(hp, seed, n_ctx):
+    """what bench.py does: weights generated on the device, then read back (GGML layout) for the CPU oracle"""
+    import llm_b200
+    m = llm_b200.Llama(hp, llm_b200.ModelParameters(context_size=n_ctx))
+    m.synthesize(seed)
+    shapes = synth.tensor_shapes(hp)
+    tens = {}
+    for k, shp in shapes.items():
+        v = m.read_tensor(k)
+        tens[k] = v.reshape(shp[0], -1) if v.dtype == np.uint8 else v
+    return m, tens
+
+
+def _cpu_model(orc, hp, tens, n_threads=16, n_batch=512):
+    """the reference's own compiled ggml.c when oracle/_ref is present (multi-threaded: 512-token prefill of 7B layers), else the port"""
+    if B.have_ref("ref"):
+        return B.RefLib("ref").llama(hp, tens, n_threads=n_threads, n_batch=n_batch)
+    return orc.llama(hp, tens)
+
+
+@pytest.mark.slow
+def test_published_config_prefill512_and_decode_at_512(orc):
+    """BASELINE.json configs[1]/[2] as bench.py runs them, on 2 layers of LLaMA-7B geometry with device-synthesised weights:
+    prefill of 512 tokens with ALL 512 logit rows compared (OutputRequest::all_logits, model/common.rs:22-39), then 5 decode steps at
+    n_past = 512..516 (CUDA-graph bucket 768, the bucket the bench decodes in), logits and both KV caches bit-identical."""
+    import llm_b200
+    hp = dict(synth.CONFIGS["7b-2l"], wtype=B.Q4_0, n_ctx=2048)
+    m, tens = _device_synth_model(hp, 0x5EED0000, 2048)
+    s = m.start_session(llm_b200.InferenceSessionConfig(n_batch=512))
+    toks = np.random.default_rng(0x70CE11).integers(0, hp["n_vocab"], 520, dtype=np.int32)       # bench.py's prompt
+    mo = _cpu_model(orc, hp, tens)
+    got = s.evaluate(toks[:512], all_logits=True)
+    check(got, mo.eval(toks[:512]), "prefill@512, all rows")
+    for i in range(512, 517):
+        g = s.evaluate(toks[i:i + 1], all_logits=True)
+        assert s.last_launches == 7 * hp["n_layer"] + 3, ("fused decode graph not used", s.last_launches)
+        check(g, mo.eval(toks[i:i + 1]), f"decode at n_past={i}")
+    for which in (0, 1):
+        a = s.kv(which)
+        assert np.array_equal(a, mo.kv(which)[:a.size]), which
+    # the bench's timed loop: rewind to 512 and decode again from device-resident state -> same bits as the first time
+    s.rewind(512)
+    again = s.evaluate(toks[512:513], all_logits=True)
+    mo.set_n_past(512)
+    check(again, mo.eval(toks[512:513]), "decode after rewind(512)")
+    s.close(); m.close(); mo.close()
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q5_1"])
+def test_decode_graph_bucket_edges(orc, name):
+    """the decode CUDA graph is captured per context bucket (256 / 768 / ...): every step across the bucket edges
+    n_past = 254..258 and 510..514 is bit-exact, and so is a prefill chunk that straddles an edge"""
+    t = B.QUANT_TYPES[name]
+    hp, tens = synth.make_llama(dict(synth.CONFIGS["small"], n_ctx=1024), t, orc.quantize)
+    toks = synth.make_tokens(hp, 530)
+    mo = _cpu_model(orc, hp, tens, n_threads=8)
+    m, s = native(hp, tens, 1024, 256)
+    check(s.evaluate(toks[:254], all_logits=True), mo.eval(toks[:254]), "prefill 254")
+    for i in range(254, 259):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"decode {i}")
+    check(s.evaluate(toks[259:510], all_logits=True), mo.eval(toks[259:510]), "prefill 259..509 (straddles 256)")
+    for i in range(510, 515):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"decode {i}")
+    check(s.evaluate(toks[515:530], all_logits=True), mo.eval(toks[515:530]), "batch 15 past 512")
+    for which in (0, 1):
+        a = s.kv(which)
+        assert np.array_equal(a, mo.kv(which)[:a.size]), which
+    s.close(); m.close(); mo.close()
+
+
+def test_rope_overrides(orc):
+    """ModelParameters::rope_overrides (frequency_base / frequency_scale) reach every RoPE of prefill and of the decode graph"""
+    import llm_b200
+    hp, tens = synth.make_llama(synth.CONFIGS["small"], B.Q4_0, orc.quantize)
+    toks = synth.make_tokens(hp, 48)
+    mo = orc.llama(hp, tens)
+    mo.set_rope(26000.0, 0.5)
+    m = llm_b200.Llama(hp, llm_b200.ModelParameters(context_size=hp["n_ctx"], rope_freq_base=26000.0, rope_freq_scale=0.5), tens)
+    s = m.start_session(llm_b200.InferenceSessionConfig(n_batch=64))
+    check(s.evaluate(toks[:40], all_logits=True), mo.eval(toks[:40]), "prefill, rope overrides")
+    for i in range(40, 44):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"decode {i}, rope overrides")
+    s.close(); m.close()
+
+
+@pytest.mark.slow
+def test_13b_geometry_two_layers_q5_1(orc):
+    """BASELINE.json configs[3] geometry (LLaMA-13B: n_embd 5120, 40 heads, n_ff 13824) in Q5_1, 2 layers: prefill 130 + decode"""
+    hp, tens = synth.make_llama(dict(synth.CONFIGS["13b"], n_layer=2, n_ctx=512), B.Q5_1, orc.quantize)
+    toks = synth.make_tokens(hp, 140)
+    mo = _cpu_model(orc, hp, tens)
+    m, s = native(hp, tens, 512, 256)
+    check(s.evaluate(toks[:130], all_logits=True), mo.eval(toks[:130]), "13b-2l prefill")
+    for i in range(130, 134):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mo.eval(toks[i:i + 1]), f"13b-2l decode {i}")
+        assert s.last_launches == 7 * hp["n_layer"] + 3
+    s.close(); m.close(); mo.close()

@@ -133,3 +133,24 @@ def test_llama_vs_reference(orc, ref, cfg, name):
     rows = np.concatenate([mr1.eval(toks[i:i + 1]) for i in range(8)])
     mo.reset()
     assert np.array_equal(bits(rows), bits(mo.eval(toks[:8])))
+
+
+def test_llama_rope_overrides_and_set_n_past_vs_reference(orc, ref):
+    """RoPEOverrides (op_rope_inplace -> ggml_rope_custom_inplace, crates/ggml/src/context.rs:558-590) and the position restore used
+    by bench.py's CPU arm: the plain-C port and the reference's compiled ggml.c agree bit for bit."""
+    hp, tens = synth.make_llama(synth.CONFIGS["tiny"], B.Q4_0, orc.quantize)
+    toks = synth.make_tokens(hp, 30)
+    mr = ref.llama(hp, tens, n_threads=3, n_batch=64)
+    mo = orc.llama(hp, tens)
+    plain = mo.eval(toks[:9]).copy()
+    mo.reset()
+    for m in (mr, mo):
+        m.set_rope(26000.0, 0.5)
+    a, b = mr.eval(toks[:20]), mo.eval(toks[:20])
+    assert np.array_equal(bits(a), bits(b))
+    assert not np.array_equal(bits(b[:9]), bits(plain))                 # the override really changes the result
+    assert np.array_equal(bits(mr.eval(toks[20:21])), bits(mo.eval(toks[20:21])))
+    # rewind both to position 12 (the cache rows 12.. are simply overwritten) and continue
+    for m in (mr, mo):
+        m.set_n_past(12)
+    assert np.array_equal(bits(mr.eval(toks[12:15])), bits(mo.eval(toks[12:15])))
