@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""bench.py -- LLaMA-7B Q4_0 tokens/sec on B200 (BASELINE.json metric), decode@1 headline + prefill@512 beside it.
+"""bench.py -- LLaMA-7B Q4_0 tokens/sec on B200 (BASELINE.json metric): decode@1 (default line) and prefill@512 (--metric prefill).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (N>1: launched by torchrun, one replica per GPU)
-  python bench.py --impl reference [...]                        the reference's own ggml CPU path on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--metric decode|prefill]    our arm (N>1: torchrun, one replica per GPU)
+  python bench.py --impl reference [--metric decode|prefill] [...]                  the reference's own ggml CPU path, FULL 32-layer model
 
 A "step" is one pass of the hot path over one batch: one decode token (Llama::evaluate with 1 token) at n_past = 512 on a
 synthetic, device-generated LLaMA-7B Q4_0 model (BASELINE.json configs[1]).  Every headline number is measured on the CONFORMANT
@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 HP_7B = dict(n_vocab=32000, n_embd=4096, n_head=32, n_head_kv=32, n_layer=32, n_rot=128, n_ff=11008, wtype=2)
 N_PAST = 512
 METRIC = "LLaMA-7B Q4_0 tokens/sec (decode@1, n_past=512)"
+METRIC_PREFILL = "LLaMA-7B Q4_0 tokens/sec (prefill@512)"
 
 
 def peaks():
@@ -96,76 +97,117 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference's own ggml.c (oracle/_ref, else the plain-C port) on the host cores
+# reference arm / cpu_baseline: the reference's own ggml.c (oracle/_ref, else the plain-C port) on the host cores, on the FULL model
 # --------------------------------------------------------------------------------------------------------------------------------
-def cpu_reference_decode(steps, warmup, sample_layers=2, log=lambda *a: None):
-    """Bounded sample of the same workload: a LLaMA-7B-geometry Q4_0 model with `sample_layers` transformer layers (+ the full
-    32000 x 4096 lm_head) decoded at n_past = 512 on the host cores; the 32-layer token time is
-    t_head + 32 * (t_sample - t_head) / sample_layers, with t_head timed as the lm_head mat-vec alone."""
+def cpu_reference(metric, steps, warmup, log=lambda *a: None, weights=None, gpu=None, n_layer=32, budget_s=240.0):
+    """The reference's ggml CPU path on the published configuration: the full `n_layer`-layer LLaMA-7B Q4_0 model (3.7 GB of blocks).
+
+    weights = None : blocks drawn directly (oracle/synth.make_llama_random_blocks; timing does not depend on the values) -- `--impl reference`.
+    weights = dict : the GPU arm's device-synthesised tensors read back (b200_model_read_tensor): the SAME model on both sides, and with
+                     gpu = dict(kv=(K, V), token=id, logits=row, n_past=512) the first CPU decode step is compared bit for bit with the
+                     GPU's logits at the same position (the cache contents are installed from the GPU session, so no 30 s CPU prefill).
+    decode : warmup + steps single-token evaluates at n_past = 512 (position restored before every step, like the GPU arm's rewind),
+             median, for several thread counts on the one loaded model -- the reference is credited with its best.
+    prefill: one 512-token evaluate from an empty session per thread count (the reference computes the lm_head on all 512 rows)."""
     from oracle import bindings as B
     from oracle import synth
     kind = "reference" if B.have_ref("ref") else "port"
     nproc = os.cpu_count() or 1
-    hp = dict(synth.CONFIGS["7b"], n_layer=sample_layers, n_ctx=N_PAST + 64)
+    hp = dict(synth.CONFIGS["7b"], n_layer=n_layer, n_ctx=2048 if gpu else N_PAST + 64, wtype=B.Q4_0)
+    t0 = time.time()
+    if weights is None:
+        hp, weights = synth.make_llama_random_blocks(hp, B.Q4_0)
+    log(f"cpu: {n_layer}-layer LLaMA-7B Q4_0 model ready in {time.time() - t0:.1f}s ({sum(v.nbytes for v in weights.values()) / 1e9:.2f} GB)")
     t0 = time.time()
     if kind == "reference":
-        ref = B.RefLib("ref")
-        quant = ref.quantize
+        m = B.RefLib("ref").llama(hp, weights, n_threads=max(1, nproc // 2), n_batch=N_PAST)
+        cands = sorted({max(1, nproc // 2), min(16, nproc), min(32, nproc)}, reverse=True)
     else:
-        orc = B.Oracle()
-        quant = orc.quantize
-    hp, tens = synth.make_llama(hp, B.Q4_0, quant)
-    log(f"cpu: synthetic {sample_layers}-layer 7B-geometry model built in {time.time() - t0:.1f}s")
-    toks = synth.make_tokens(hp, N_PAST + 1)
-    best = None
-    # thread counts to try (all hyper-threads: the reference's spin barrier collapses, 5 s/token); the barrier is also sensitive to whatever else runs on
-    # the box, so every count is tried twice and the reference is credited with its best
-    cands = sorted({max(1, nproc // 2), min(8, nproc), min(16, nproc), min(32, nproc)}) if kind == "reference" else [nproc]
-    for nt in list(cands) + (list(cands) if kind == "reference" and nproc > 8 else []):
+        m = B.Oracle().llama(hp, weights)
+        cands = [nproc]
+    log(f"cpu[{kind}]: model loaded in {time.time() - t0:.1f}s; host has {nproc} logical cores; thread counts to try: {cands}")
+    toks = synth.make_tokens(hp, N_PAST + 1) if gpu is None else None
+    t_start = time.time()
+    out = dict(kind=kind, unit="tokens/s", parity=None)
+
+    def set_threads(nt):
         if kind == "reference":
-            m = ref.llama(hp, tens, n_threads=nt, n_batch=N_PAST)
+            m.set_threads(nt)
         else:
             os.environ["OMP_NUM_THREADS"] = str(nt)
-            m = orc.llama(hp, tens)
-        t0 = time.time()
-        m.eval(toks[:N_PAST])                     # fill the KV cache (CPU prefill of the sample)
-        t_prefill = time.time() - t0
-        ts = []
-        for i in range(warmup + steps):          # n_past walks 512, 513, ... (the harness has no rewind); n_ctx leaves room for 64 steps
+
+    if metric == "prefill":
+        best = None
+        for nt in cands[:2]:
+            set_threads(nt)
+            m.set_n_past(0)
             t0 = time.time()
-            m.eval(toks[N_PAST:N_PAST + 1])
-            ts.append(time.time() - t0)
-        t_sample = statistics.median(ts[warmup:])
-        # embedding + final norm + lm_head alone: the same model with zero transformer layers
-        hp0 = dict(hp, n_layer=0)
-        tens0 = {k: v for k, v in tens.items() if not k.startswith("layers.")}
-        m0 = ref.llama(hp0, tens0, n_threads=nt, n_batch=8) if kind == "reference" else orc.llama(hp0, tens0)
-        th = []
-        for i in range(warmup + steps):
-            t0 = time.time()
-            m0.eval(toks[N_PAST:N_PAST + 1])
-            th.append(time.time() - t0)
-        m0.close()
-        t_head = min(statistics.median(th[warmup:]), t_sample * 0.95)
-        t_tok = t_head + 32 * (t_sample - t_head) / sample_layers
-        log(f"cpu[{kind}] threads={nt}: sample step {t_sample * 1e3:.1f} ms, lm_head {t_head * 1e3:.1f} ms -> 32-layer token {t_tok * 1e3:.1f} ms; sample prefill@512 {t_prefill:.1f}s")
-        if best is None or t_tok < best["t_tok"]:
-            best = dict(t_tok=t_tok, threads=nt, t_sample=t_sample, t_head=t_head, t_prefill_sample=t_prefill)
+            m.eval(toks[:N_PAST])
+            dt = time.time() - t0
+            log(f"cpu[{kind}] threads={nt}: prefill@512 {dt:.2f} s")
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+            if time.time() - t_start > budget_s:
+                break
+        out.update(value=N_PAST / best[0], cores=best[1], ms_per_step=best[0] * 1e3,
+                   sample=f"full {n_layer}-layer LLaMA-7B Q4_0, one 512-token evaluate from an empty session (lm_head on all 512 rows, as the reference does), best of {len(cands[:2])} thread counts; host has {nproc} logical cores")
         m.close()
-    return dict(value=1.0 / best["t_tok"], unit="tokens/s", cores=best["threads"], kind=kind,
-                sample=f"{sample_layers}-layer LLaMA-7B-geometry Q4_0 model + full lm_head, decode at n_past~{N_PAST}, median of {steps} steps; "
-                       f"token time = t_head + 32*(t_sample - t_head)/{sample_layers} (t_sample {best['t_sample'] * 1e3:.1f} ms, t_head {best['t_head'] * 1e3:.1f} ms); host has {nproc} logical cores",
-                ms_per_step=best["t_tok"] * 1e3)
+        return out
+
+    # ---- decode ----
+    one = None
+    if gpu is not None:                                        # install the GPU session's KV cache: same model, same state, same token
+        for which in (0, 1):
+            dst, nbytes = m.kv_ptr(which)
+            src = gpu["kv"][which]
+            assert src.nbytes <= nbytes, (src.nbytes, nbytes)
+            C.memmove(dst, src.ctypes.data, src.nbytes)
+        one = np.array([gpu["token"]], np.int32)
+    else:
+        set_threads(cands[0])
+        t0 = time.time()
+        m.eval(toks[:N_PAST])                                  # a real prefill fills the cache
+        out["prefill_ms"] = (time.time() - t0) * 1e3
+        log(f"cpu[{kind}] threads={cands[0]}: prefill@512 {out['prefill_ms'] / 1e3:.2f} s (fills the KV cache)")
+        one = toks[N_PAST:N_PAST + 1]
+    logits = np.empty((1, hp["n_vocab"]), np.float32)
+    if gpu is not None:
+        set_threads(cands[0])
+        m.set_n_past(gpu["n_past"])
+        m.eval_into(one, logits)
+        same = np.array_equal(logits[0].view(np.uint32), gpu["logits"].view(np.uint32))
+        out["parity"] = {"checked": f"decode step at n_past={gpu['n_past']}, full {n_layer}-layer model, device-synthesised weights read back, KV cache installed from the GPU session",
+                         "bit_identical": bool(same), "max_abs_diff": float(np.abs(logits[0] - gpu["logits"]).max())}
+        log(f"parity at the published configuration: logits bit-identical = {same}")
+    best = None
+    for nt in cands:
+        set_threads(nt)
+        ts = []
+        for i in range(warmup + steps):
+            m.set_n_past(N_PAST)
+            t0 = time.time()
+            m.eval_into(one, logits)
+            ts.append(time.time() - t0)
+        t_tok = statistics.median(ts[warmup:])
+        log(f"cpu[{kind}] threads={nt}: decode at n_past=512: {t_tok * 1e3:.1f} ms/token")
+        if best is None or t_tok < best[0]:
+            best = (t_tok, nt)
+        if time.time() - t_start > budget_s:
+            break
+    out.update(value=1.0 / best[0], cores=best[1], ms_per_step=best[0] * 1e3,
+               sample=f"full {n_layer}-layer LLaMA-7B Q4_0, single-token evaluates at n_past=512, median of {steps} steps after {warmup} warm-up, best of the thread counts {cands}; host has {nproc} logical cores")
+    m.close()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--metric", default="decode", choices=["decode", "prefill"], help="which half of BASELINE.json's metric the JSON line reports")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is NOT the benchmark config")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON); libraries that print to fd 1 (e.g. NCCL's version banner) are sent to stderr
@@ -178,20 +220,27 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    steps, warmup = args.steps, max(3, args.warmup)
+    prefill_metric = args.metric == "prefill"
+    steps = args.steps if args.steps else (10 if prefill_metric else 64)
+    warmup = max(3, args.warmup if args.warmup is not None else (3 if prefill_metric else 8))
+    metric_name = METRIC_PREFILL if prefill_metric else METRIC
+    workload = ("LLaMA-7B Q4_0 prefill batch=512 from an empty session (BASELINE.json configs[2])" if prefill_metric
+                else "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1])")
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        rsteps = min(steps, 12)
-        cb = cpu_reference_decode(rsteps, min(warmup, 3), log=log)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": rsteps,
-                "warmup": min(warmup, 3), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        rsteps, rwarm = (1, 0) if prefill_metric else (min(steps, 12), min(warmup, 3))
+        cb = cpu_reference(args.metric, rsteps, rwarm, log=log, n_layer=args.layers)
+        line = {"impl": "reference", "metric": metric_name, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": rsteps,
+                "warmup": rwarm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8xint8->f32 (Q4_0 x Q8_0 blocks)", "data": "synthetic",
-                "config": {"workload": "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1]), reference ggml CPU path", "l2": "n/a (CPU)"},
+                "config": {"workload": workload + ", reference ggml CPU path", "n_layer": args.layers, "l2": "n/a (CPU)"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        if "prefill_ms" in cb:
+            line["prefill_ms"] = cb["prefill_ms"]
         emit(line)
         return
 
@@ -213,6 +262,7 @@ def main():
     sess = model.start_session(llm_b200.InferenceSessionConfig(n_batch=512))
     rng = np.random.default_rng(0x70CE11 + rank)
     prompt = rng.integers(0, hp["n_vocab"], N_PAST + 1, dtype=np.int32)
+    pk = peaks()
 
     def barrier():
         if dist is not None:
@@ -221,70 +271,89 @@ def main():
             torch.cuda.synchronize()
         sess.sync()
 
-    # prefill@512 (also fills the KV cache for the decode steps)
-    prefill = None
-    reps = 1 if args.no_prefill else 5
-    pf_ms = []
-    for r in range(reps + 1):
+    def allmax(*vals):
+        if dist is None:
+            return vals
+        import torch
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t)
+
+    # ---- prefill@512 (also fills the KV cache for the decode steps) -------------------------------------------------------------------
+    tok512 = np.ascontiguousarray(prompt[:N_PAST])
+    last_row = np.empty(hp["n_vocab"], np.float32)
+    p_steps, p_warm = (steps, warmup) if prefill_metric else (4, 2)
+    for _ in range(p_warm):                                           # the first call uploads the tokens; they stay in HBM for the device-resident arm
         sess.rewind(0)
-        tok = np.ascontiguousarray(prompt[:N_PAST])
-        L.b200_timing_begin()
-        rc = L.b200_session_evaluate(sess._s, tok.ctypes.data, N_PAST, None, 0)
-        ms = L.b200_timing_end_ms()
-        assert rc == 0, rc
-        if r > 0 or reps == 1:
-            pf_ms.append(ms)
+        assert L.b200_session_evaluate(sess._s, tok512.ctypes.data, N_PAST, None, 0) == 0
     pf_launches = sess.last_launches
-    if not args.no_prefill:
-        ms = statistics.median(pf_ms)
-        fl = prefill_flops(hp, N_PAST)
-        pk = peaks()
-        prefill = {"value": N_PAST / (ms * 1e-3), "unit": "tokens/s", "ms": ms, "reps": reps, "launches": pf_launches,
-                   "tensor_frac_of_bf16_sustained": fl / (ms * 1e-3) / (pk["bf16_sustained"] * 1e12),
-                   "note": "conformant (bit-exact) path: block dots on tensor cores (block-diagonal f16 MMA), AVX2-order f32 lane chains on the fp32 pipe; includes attention and the 2 KB token upload; lm_head on the last row only (OutputRequest without all_logits)"}
-        log(f"prefill@512: {ms:.2f} ms -> {prefill['value']:.0f} tok/s ({pf_launches} kernels)")
-
-    # ---- non-conformant fast mode (order-free kernels), reported separately ----
-    fast_mode = None
-    if not args.no_prefill and world == 1:
-        fs = model.start_session(llm_b200.InferenceSessionConfig(n_batch=512, flags=4))
-        tokp = np.ascontiguousarray(prompt[:N_PAST])
-        fms = []
-        for r in range(4):
-            fs.rewind(0)
-            L.b200_timing_begin()
-            assert L.b200_session_evaluate(fs._s, tokp.ctypes.data, N_PAST, None, 0) == 0
-            fms.append(L.b200_timing_end_ms())
-        f_pf = statistics.median(fms[1:])
-        onef = np.ascontiguousarray(prompt[N_PAST:N_PAST + 1])
-        assert L.b200_session_evaluate(fs._s, onef.ctypes.data, 1, None, 0) == 0
-        f_launch = fs.last_launches
-        for _ in range(warmup):
-            fs.rewind(N_PAST); L.b200_session_evaluate_device(fs._s, None, 1)
+    barrier()
+    with ClockSampler(local_rank) as pclk:
         L.b200_timing_begin()
-        for _ in range(steps):
-            fs.rewind(N_PAST); L.b200_session_evaluate_device(fs._s, None, 1)
-        f_dec = L.b200_timing_end_ms() / steps
-        fl = prefill_flops(hp, N_PAST)
-        fast_mode = {"conformant": False,
-                     "note": "integer-exact block dots, free f32 summation order: <=2e-6 per mat-mul, ~1e-2 on logits (the reference's own sensitivity to re-association, tests/test_chaos.py)",
-                     "decode_tokens_per_s": 1e3 / f_dec, "decode_ms": f_dec, "decode_launches": f_launch,
-                     "prefill_tokens_per_s": N_PAST / (f_pf * 1e-3), "prefill_ms": f_pf,
-                     "prefill_tensor_frac_of_bf16_sustained": fl / (f_pf * 1e-3) / (peaks()["bf16_sustained"] * 1e12)}
-        log(f"fast mode (non-conformant): decode {1e3 / f_dec:.0f} tok/s, prefill@512 {f_pf:.2f} ms")
-        fs.close()
+        for _ in range(p_steps):                                      # device-resident: token ids and logits stay in HBM
+            sess.rewind(0)
+            L.b200_session_evaluate_device(sess._s, None, N_PAST)
+        pf_dev = L.b200_timing_end_ms()
+        barrier()
+        t0 = time.perf_counter()
+        L.b200_timing_begin()
+        for _ in range(p_steps):                                      # e2e: host token ids in (2 KB), last-row logits out (128 KB), sync, every step
+            sess.rewind(0)
+            L.b200_session_evaluate(sess._s, tok512.ctypes.data, N_PAST, last_row.ctypes.data, 0)
+        pf_e2e = max(L.b200_timing_end_ms(), (time.perf_counter() - t0) * 1e3)
+        barrier()
+    pf_clocks = pclk.summary()
+    pf_dev, pf_e2e = allmax(pf_dev, pf_e2e)
+    fl = prefill_flops(hp, N_PAST)
+    pf_ms = pf_dev / p_steps
+    # kernel-only timing of the weight GEMMs of one pass (the dominant kernel), on synthetic operands of the same shapes
+    gemm = None
+    if rank == 0:
+        L.b200_op_bench_mul_mat.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+        impl = 7 if os.environ.get("B200_PREFILL_GEMM", "tc5") != "mma" else 6
+        e, f, v = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
+        tot_ms, tot_fl, n_l = 0.0, 0.0, 0
+        for K, N, cnt, B in ((e, 3 * e, hp["n_layer"], N_PAST), (e, e, hp["n_layer"], N_PAST), (e, 2 * f, hp["n_layer"], N_PAST), (f, e, hp["n_layer"], N_PAST)):
+            if cnt == 0:
+                continue
+            ms = C.c_float()
+            assert L.b200_op_bench_mul_mat(hp["wtype"], K, N, B, impl, 5, C.byref(ms)) == 0
+            tot_ms += ms.value * cnt; tot_fl += 2.0 * B * N * K * cnt; n_l += cnt
+        gemm = dict(ms=tot_ms, flops=tot_fl, launches=n_l, impl=impl)
+    prefill = {"value": world * N_PAST / (pf_ms * 1e-3), "unit": "tokens/s", "ms": pf_ms, "steps": p_steps, "launches": pf_launches,
+               "e2e": {"value": world * N_PAST / (pf_e2e / p_steps * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * N_PAST, "d2h_bytes_per_step": 4 * hp["n_vocab"],
+                       "ms_per_step": pf_e2e / p_steps},
+               "step_roofline": {"bound": "tensor", "flops_per_step": fl, "achieved": fl / (pf_ms * 1e-3) / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                 "frac": fl / (pf_ms * 1e-3) / 1e12 / pk["bf16_sustained"], "peak_source": pk["source"] + " (cuBLAS bf16, sustained)"},
+               "clocks": pf_clocks,
+               "note": "conformant (bit-exact) path; includes attention; lm_head on the last row only (OutputRequest without all_logits) -- the reference computes all 512 rows"}
+    if gemm:
+        # exact-order floor: 9 fp32 operations per (token, row, 32-block) -- the reference's own rounding sequence -- on 148 SMs x 128 lanes
+        fp32_floor_ms = 9.0 * gemm["flops"] / 64.0 / (148 * 128 * (pf_clocks.get("sm_mhz") or 1965.0) * 1e6) * 1e3
+        prefill["roofline"] = {"bound": "tensor", "kernel": ("mm_exact_tc5_kernel<Q4_0> (tcgen05.mma + TMEM + TMA)" if gemm["impl"] == 7 else "mm_exact_mma_kernel<Q4_0> (mma.sync)") +
+                               f": the {gemm['launches']} per-layer weight GEMMs of one 512-token pass, timed alone on operands of the same shapes",
+                               "achieved": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                               "frac": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / pk["bf16_sustained"], "peak_source": pk["source"] + " (cuBLAS bf16, sustained)",
+                               "traffic": None, "launches": gemm["launches"], "ms_per_pass": gemm["ms"], "share_of_step": gemm["ms"] / pf_ms,
+                               "exact_order_fp32_floor_ms": fp32_floor_ms, "frac_of_exact_order_floor": fp32_floor_ms / gemm["ms"],
+                               "note": "useful flops 2*B*N*K; the bit-exact kernel runs block-diagonal MMAs (4x the useful tensor work) and is bound by the reference's ordered fp32 chain, not the tensor pipe"}
+    log(f"prefill@512: {pf_ms:.2f} ms device-resident ({prefill['value']:.0f} tok/s), e2e {pf_e2e / p_steps:.2f} ms, {pf_launches} kernels" +
+        (f"; weight GEMMs alone {gemm['ms']:.1f} ms" if gemm else ""))
 
-    # decode@1 at n_past = 512: device-resident arm
+    # ---- decode@1 at n_past = 512 -------------------------------------------------------------------------------------------------------
+    d_steps, d_warm = (steps, warmup) if not prefill_metric else (16, 4)
     one = np.ascontiguousarray(prompt[N_PAST:N_PAST + 1])
-    assert L.b200_session_evaluate(sess._s, one.ctypes.data, 1, None, 0) == 0      # leaves the token id in HBM
+    sess.rewind(0)
+    assert L.b200_session_evaluate(sess._s, tok512.ctypes.data, N_PAST, None, 0) == 0      # KV cache of positions 0..511
+    assert L.b200_session_evaluate(sess._s, one.ctypes.data, 1, None, 0) == 0              # leaves the token id in HBM
     launches_per_step = sess.last_launches
-    for _ in range(warmup):
+    for _ in range(d_warm):
         sess.rewind(N_PAST)
         assert L.b200_session_evaluate_device(sess._s, None, 1) == 0
     barrier()
     with ClockSampler(local_rank) as clk:
         L.b200_timing_begin()
-        for _ in range(steps):
+        for _ in range(d_steps):
             sess.rewind(N_PAST)
             L.b200_session_evaluate_device(sess._s, None, 1)
         ms_dev = L.b200_timing_end_ms()
@@ -297,7 +366,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         L.b200_timing_begin()
-        for _ in range(steps):
+        for _ in range(d_steps):
             sess.rewind(N_PAST)
             L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0)
         ms_e2e = L.b200_timing_end_ms()
@@ -306,57 +375,68 @@ def main():
         barrier()
         # roofline probe of the dominant kernel (quantized mat-vec) on the real weights
         nl, nbytes = C.c_int64(0), C.c_double(0)
-        probe_reps = 3
-        ms_probe = L.b200_session_probe_matvec(sess._s, probe_reps, C.byref(nl), C.byref(nbytes))
+        ms_probe = L.b200_session_probe_matvec(sess._s, 3, C.byref(nl), C.byref(nbytes))
     clocks = clk.summary()
     assert np.isfinite(logits).all()
-
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e = allmax(ms_dev, ms_e2e)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
     wbytes, kvbytes, embbytes = algorithmic_bytes_per_token(hp, N_PAST)
     tok_bytes = wbytes + kvbytes + embbytes
-    value = world * steps / (ms_dev * 1e-3)
-    e2e = world * steps / (ms_e2e * 1e-3)
     probe_gbs = nbytes.value / (ms_probe * 1e-3) / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/s8 block dots -> f32 (Q4_0 weights x Q8_0 activations)", "data": "synthetic",
-        "config": {"workload": "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1])", "n_layer": hp["n_layer"], "n_ctx": 2048,
-                   "kv_cache": "f16", "parallelism": f"{world} independent replica(s), no collective",
-                   "l2": "inputs larger than L2: 3.7 GB of weights streamed per step vs 126 MB L2",
-                   "weights": "random-init, generated on device (N(0,1/K) -> Q4_0 by the reference's quantizer rule)"},
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 * hp["n_vocab"], "ms_per_step": ms_e2e / steps},
-        "gpu_launches": launches_per_step * steps,
-        "launches_per_step": launches_per_step,
-        "roofline": {"bound": "hbm", "kernel": "mmv_exact_stream_kernel<Q4_0>: all 129 weight mat-vecs of the model back to back, timed alone (the dominant kernel: 93% of a token's bytes)",
+    decode = {
+        "value": world * d_steps / (ms_dev * 1e-3), "unit": "tokens/s", "ms": ms_dev / d_steps, "steps": d_steps, "launches_per_step": launches_per_step,
+        "e2e": {"value": world * d_steps / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 * hp["n_vocab"], "ms_per_step": ms_e2e / d_steps},
+        "roofline": {"bound": "hbm", "kernel": "mmv_exact_stream_kernel<Q4_0> (the stand-alone form of the mmv_fused_kernel<Q4_0,EPI> instances of the decode graph: same core loop, "
+                                             "no fused epilogue): all 129 weight mat-vecs of the model back to back, timed alone (93% of a token's bytes)",
                      "achieved": probe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": probe_gbs / pk["hbm_gbs"], "peak_source": pk["source"] + " (burst copy)",
-                     # ncu --set full (profiles/r01c_mmv_fused.ncu-rep): dram__bytes_read of a mat-vec launch = 1.0015 x its algorithmic bytes, no writes to speak of
+                     # ncu --set full (profiles/r01h_mmv_fused.ncu-rep): dram__bytes_read of a mat-vec launch = 1.0015 x its algorithmic bytes, no writes to speak of
                      "traffic": nbytes.value / max(1, nl.value) * 1.0015, "traffic_source": "ncu dram__bytes_read+write per launch, scaled from the captured w13 launch (50.80 MB vs 50.72 MB algorithmic)",
                      "launches": int(nl.value), "avg_launch_us": ms_probe * 1e3 / max(1, nl.value),
                      "algorithmic_bytes_per_launch": nbytes.value / max(1, nl.value)},
-        "step_roofline": {"bytes_per_token": tok_bytes, "weights": wbytes, "kv": kvbytes, "achieved_gbs": tok_bytes / (ms_dev / steps * 1e-3) / 1e9,
-                          "frac": tok_bytes / (ms_dev / steps * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "step_roofline": {"bound": "hbm", "bytes_per_token": tok_bytes, "weights": wbytes, "kv": kvbytes, "achieved_gbs": tok_bytes / (ms_dev / d_steps * 1e-3) / 1e9,
+                          "frac": tok_bytes / (ms_dev / d_steps * 1e-3) / 1e9 / pk["hbm_gbs"]},
         "clocks": clocks,
     }
-    line["conformance"] = "logits bit-identical to the reference ggml CPU path (tests/test_gpu_llama.py); decode schedule: 7 fused kernels/layer (attention = one cluster launch) replayed from one CUDA graph"
-    if prefill:
-        line["prefill"] = prefill
-    if fast_mode:
-        line["fast_mode"] = fast_mode
+    log(f"decode@1 n_past=512: {decode['ms']:.3f} ms/token device-resident ({decode['value']:.0f} tok/s), e2e {ms_e2e / d_steps:.3f} ms; {launches_per_step} kernels per token")
+    main_part, other_key, other = (prefill, "decode", decode) if prefill_metric else (decode, "prefill", prefill)
+    line = {
+        "metric": metric_name, "value": main_part["value"], "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": main_part["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/s8 block dots -> f32 (Q4_0 weights x Q8_0 activations)", "data": "synthetic",
+        "config": {"workload": workload, "n_layer": hp["n_layer"], "n_ctx": 2048,
+                   "kv_cache": "f16", "parallelism": f"{world} independent replica(s), no collective",
+                   "l2": "inputs larger than L2: 3.7 GB of weights streamed per step vs 126 MB L2",
+                   "weights": "random-init, generated on device (N(0,1/K) -> Q4_0 by the reference's quantizer rule)"},
+        "e2e": main_part["e2e"],
+        "gpu_launches": (pf_launches if prefill_metric else launches_per_step) * steps,
+        "launches_per_step": pf_launches if prefill_metric else launches_per_step,
+        "roofline": main_part.get("roofline"), "step_roofline": main_part["step_roofline"], "clocks": main_part["clocks"],
+        other_key: other,
+        "conformance": "kernels reproduce the reference's AVX2 operation order: logits and KV cache bit-identical to the reference ggml CPU path "
+                       "(tests/test_gpu_llama.py::test_published_config_prefill512_and_decode_at_512; cpu_baseline.parity below for this very run)",
+    }
     if not args.no_cpu_baseline and world == 1:
         try:
-            cb = cpu_reference_decode(6, 2, log=log)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # the SAME model on the CPU: device-synthesised weights read back in GGML layout, the session's KV cache installed, one step compared
+            from oracle import synth
+            t0 = time.time()
+            weights = {}
+            for k, shp in synth.tensor_shapes(hp).items():
+                v = model.read_tensor(k)
+                weights[k] = v.reshape(shp[0], -1) if v.dtype == np.uint8 else v
+            sess.rewind(N_PAST)
+            gpu_logits = np.empty(hp["n_vocab"], np.float32)
+            assert L.b200_session_evaluate(sess._s, one.ctypes.data, 1, gpu_logits.ctypes.data, 0) == 0
+            gpu = dict(kv=(sess.kv(0), sess.kv(1)), token=int(one[0]), logits=gpu_logits, n_past=N_PAST)
+            log(f"weights + KV cache read back in {time.time() - t0:.1f}s")
+            cb = cpu_reference("decode", 6, 2, log=log, weights=weights, gpu=gpu, n_layer=hp["n_layer"], budget_s=45.0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "parity")}
+            if prefill_metric:
+                line["cpu_baseline"]["note"] = "decode@1 tokens/s of the reference on this host (the bounded sample); its prefill@512 is the --impl reference --metric prefill line"
         except Exception as ex:                                       # the baseline leg must never take the GPU number down
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
     emit(line)

@@ -33,11 +33,13 @@ using namespace tc5;
 
 constexpr int TM = 128, TN = 32, NST = 4, DWR = 2 * NST + 4;     // tokens / rows per CTA, pipeline stages (2 blocks each), scale ring (blocks)
 constexpr int A_STAGE = TM * 64 * 2;                              // 16 KB: [128 tokens][64 elements] f16, 128-byte rows, swizzled
-constexpr int B_HALF = 128 * 16 * 2;                              // 4 KB: one block-diagonal operand (N = 128 columns x K = 16), no swizzle
+constexpr int B_LBO = 128, B_SBO = 272;                           // K-adjacent core matrices contiguous; 8-column groups 272 B apart (the expanders' 8-byte
+                                                                  // stores then spread over the banks: 2-way instead of 8-way conflicts with 256)
+constexpr int B_HALF = 16 * B_SBO;                                // one block-diagonal operand (N = 128 columns x K = 16), no swizzle
 constexpr int B_STAGE = 4 * B_HALF;                               // [block j][half h]
-constexpr int B_LBO = 128, B_SBO = 256;                           // K-adjacent core matrices contiguous, 8-column groups 256 B apart
+constexpr int XR = NST + 2, X_STAGE = TM * 16;                    // ring of per-stage activation scales: [token] float4 {d, aux} x 2 blocks
 constexpr int NTHREADS = 384;
-constexpr int SMEM_BYTES = 1024 + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + 256;
+constexpr int SMEM_BYTES = 1024 + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + XR * X_STAGE + 256;
 
 template <int TYPE> struct Tc {
     static constexpr bool MIN = (TYPE == T_Q4_1 || TYPE == T_Q5_1), QH = (TYPE == T_Q5_0 || TYPE == T_Q5_1), Q8 = (TYPE == T_Q8_0);
@@ -58,16 +60,17 @@ __device__ __forceinline__ uint32_t bytes_to_half2(uint32_t v, uint32_t sel, uin
 struct WRaw { uint4 q; uint32_t dm; uint32_t qh; };               // one (row, block) as fetched by an expander thread
 
 template <int TYPE>
-__global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, const QWeight w, const float2 *__restrict__ xds,
+__global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, const QWeight w, const float4 *__restrict__ xdt,
                                                                    float *__restrict__ dst, int64_t ldd, int64_t B, const float *__restrict__ addend, int64_t lda) {
     using T = Tc<TYPE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;                     // 128B-swizzled tiles need 1024-byte alignment
     uint8_t *const sptr = smem_raw + (sbase - smem_u32(smem_raw));
-    const uint32_t sA = sbase, sB = sbase + NST * A_STAGE, sW = sB + NST * B_STAGE, sBar = sW + DWR * TN * 8;
+    const uint32_t sA = sbase, sB = sbase + NST * A_STAGE, sW = sB + NST * B_STAGE, sX = sW + DWR * TN * 8, sBar = sX + XR * X_STAGE;
     uint8_t *const pB = sptr + NST * A_STAGE;
     float2 *const pW = (float2 *)(sptr + NST * (A_STAGE + B_STAGE));
-    uint32_t *const pTmem = (uint32_t *)(sptr + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + 128);
+    const float4 *const pX = (const float4 *)(sptr + NST * (A_STAGE + B_STAGE) + DWR * TN * 8);
+    uint32_t *const pTmem = (uint32_t *)(sptr + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + XR * X_STAGE + 128);
     auto bar_a_full = [&](int s) { return sBar + 8 * s; };
     auto bar_b_full = [&](int s) { return sBar + 8 * (NST + s); };
     auto bar_empty = [&](int s) { return sBar + 8 * (2 * NST + s); };
@@ -95,15 +98,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
     bool dead = false;
 
     if (warp < 4) {
-        reg_dealloc<72>();
+        reg_dealloc<64>();
         if (warp == 0) {
             // ================= TMA producer =================
             if (lane == 0) {
+                const uint32_t x_bytes = (uint32_t)(B - m_base < TM ? B - m_base : TM) * 16u;
                 for (int st = 0; st < nstage; st++) {
                     const int slot = st % NST; const uint32_t par = (st / NST) & 1;
                     mbar_wait(bar_empty(slot), par ^ 1, dead);
-                    mbar_expect_tx(bar_a_full(slot), A_STAGE);
+                    mbar_expect_tx(bar_a_full(slot), A_STAGE + x_bytes);
                     tma_load_2d(sA + slot * A_STAGE, &tmap_x, st * 64, (int)m_base, bar_a_full(slot));
+                    // {d, aux} of this stage's two blocks for the tile's tokens: one contiguous piece of the block-pair-major scale array.  Ring of
+                    // NST + 2 stages: slot st % XR is rewritten only after the MMAs of stage st - NST completed, i.e. after the epilogue has finished
+                    // stage st - NST - 1 (the tensor core cannot run further ahead than the two TMEM buffers)
+                    bulk_load(sX + (st % XR) * X_STAGE, xdt + ((size_t)st * B + m_base), x_bytes, bar_a_full(slot));
                 }
             }
         } else if (warp == 1) {
@@ -192,10 +200,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
         }
     } else {
         // ================= epilogue: thread = token (TMEM lane), 16 rows x 8 lanes =================
-        reg_alloc<216>();
-        const int q = warp & 3, ch = (warp - 4) >> 2;
-        const int64_t m = m_base + q * 32 + lane;
-        const float2 *xp = xds + (size_t)(m < B ? m : B - 1) * nb;
+        // Software pipeline over "chunks" (4 rows = 2 x 16 TMEM columns): iteration g waits for the loads of chunk g (issued one iteration
+        // earlier), issues the loads of chunk g + 1 -- tcgen05.ld and the rows' weight scales -- and only then runs the fp32 chain of chunk g,
+        // so the TMEM / shared-memory latency hides behind 20 arithmetic instructions of the same warp (and the SM's other 7 epilogue warps).
+        reg_alloc<224>();
+        const int q = warp & 3, ch = (warp - 4) >> 2, tok = q * 32 + lane;
+        const int64_t m = m_base + tok;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ch * 64;
         float2 acc[16][4];
         float summs[16];
@@ -204,43 +214,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
 #pragma unroll
             for (int p = 0; p < 4; p++) acc[r][p] = make_float2(0.f, 0.f); }
 
-        float4 xd = *(const float4 *)xp;                                                           // {d, aux} of blocks 0, 1 (nb is even: 16-byte aligned)
-        for (int st = 0; st < nstage; st++) {
-            float4 xd_next = xd;
-            if (st + 1 < nstage) xd_next = *(const float4 *)(xp + 2 * (st + 1));
+        uint32_t dA[32], dB[32];                                                                   // TMEM staging, double-buffered: {lanes 0-3 | lanes 4-7} x 4 rows
+        float4 wA[2], wB[2];                                                                       // {d, m} of the chunk's 4 rows
+        auto issue = [&](int blk, int c, uint32_t (&d)[32], float4 (&wv)[2]) {
+            const int buf = blk & 1;
+            if (c == 0) { mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead); tc_fence_after(); }
+            tmem_ld_x16(t_lane + buf * 256 + c * 16, *(uint32_t(*)[16])&d[0]);
+            tmem_ld_x16(t_lane + buf * 256 + 128 + c * 16, *(uint32_t(*)[16])&d[16]);
+            const float4 *wrow = (const float4 *)(pW + (blk % DWR) * TN + ch * 16 + c * 4);
+            wv[0] = wrow[0]; wv[1] = wrow[1];
+        };
+        auto compute = [&](int c, const uint32_t (&d)[32], const float4 (&wv)[2], float dx, float sx) {
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int blk = 2 * st + j, buf = blk & 1;
-                const float dx = j ? xd.z : xd.x, sx = j ? xd.w : xd.y;
-                const float2 *wrow = pW + (blk % DWR) * TN + ch * 16;
-                mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 4; c++) {                                                      // 4 rows per chunk
-                    uint32_t d0[16], d1[16];
-                    tmem_ld_x16(t_lane + buf * 256 + c * 16, d0);                                  // lanes 0-3 of rows 4c..4c+3
-                    tmem_ld_x16(t_lane + buf * 256 + 128 + c * 16, d1);                            // lanes 4-7
-                    tc_wait_ld();
-                    if (c == 3) {                                                                  // every column of this buffer has been read
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_t_empty(buf));
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 4; rr++) {
-                        const int r = c * 4 + rr;
-                        const float2 dm = wrow[r];
-                        const float s = __fmul_rn(dm.x, dx);
-                        const float2 s2 = make_float2(s, s);
-                        acc[r][0] = ffma2(s2, make_float2(__uint_as_float(d0[rr * 4 + 0]), __uint_as_float(d0[rr * 4 + 1])), acc[r][0]);
-                        acc[r][1] = ffma2(s2, make_float2(__uint_as_float(d0[rr * 4 + 2]), __uint_as_float(d0[rr * 4 + 3])), acc[r][1]);
-                        acc[r][2] = ffma2(s2, make_float2(__uint_as_float(d1[rr * 4 + 0]), __uint_as_float(d1[rr * 4 + 1])), acc[r][2]);
-                        acc[r][3] = ffma2(s2, make_float2(__uint_as_float(d1[rr * 4 + 2]), __uint_as_float(d1[rr * 4 + 3])), acc[r][3]);
-                        if (T::MIN) summs[r] = __fmaf_rn(dm.y, sx, summs[r]);
-                    }
-                }
+            for (int rr = 0; rr < 4; rr++) {
+                const int r = c * 4 + rr;
+                const float dw = rr == 0 ? wv[0].x : rr == 1 ? wv[0].z : rr == 2 ? wv[1].x : wv[1].z;
+                const float mw = rr == 0 ? wv[0].y : rr == 1 ? wv[0].w : rr == 2 ? wv[1].y : wv[1].w;
+                const float s = __fmul_rn(dw, dx);
+                const float2 s2 = make_float2(s, s);
+                acc[r][0] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 0]), __uint_as_float(d[rr * 4 + 1])), acc[r][0]);
+                acc[r][1] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 2]), __uint_as_float(d[rr * 4 + 3])), acc[r][1]);
+                acc[r][2] = ffma2(s2, make_float2(__uint_as_float(d[16 + rr * 4 + 0]), __uint_as_float(d[16 + rr * 4 + 1])), acc[r][2]);
+                acc[r][3] = ffma2(s2, make_float2(__uint_as_float(d[16 + rr * 4 + 2]), __uint_as_float(d[16 + rr * 4 + 3])), acc[r][3]);
+                if (T::MIN) summs[r] = __fmaf_rn(mw, sx, summs[r]);
             }
-            xd = xd_next;
+        };
+        auto release = [&](int blk) {                                                              // every column of the block's buffer is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_empty(blk & 1));
+        };
+
+        if (nstage > 0) issue(0, 0, dA, wA);
+        for (int st = 0; st < nstage; st++) {
+            // the scales of this stage (landed with the stage's activations, before its MMAs ran)
+            const float4 xd = pX[(st % XR) * TM + tok];
+            const bool more = st + 1 < nstage;
+            const int b0 = 2 * st, b1 = 2 * st + 1;
+            tc_wait_ld(); issue(b0, 1, dB, wB); compute(0, dA, wA, xd.x, xd.y);
+            tc_wait_ld(); issue(b0, 2, dA, wA); compute(1, dB, wB, xd.x, xd.y);
+            tc_wait_ld(); issue(b0, 3, dB, wB); compute(2, dA, wA, xd.x, xd.y);
+            tc_wait_ld(); release(b0); issue(b1, 0, dA, wA); compute(3, dB, wB, xd.x, xd.y);
+            tc_wait_ld(); issue(b1, 1, dB, wB); compute(0, dA, wA, xd.z, xd.w);
+            tc_wait_ld(); issue(b1, 2, dA, wA); compute(1, dB, wB, xd.z, xd.w);
+            tc_wait_ld(); issue(b1, 3, dB, wB); compute(2, dA, wA, xd.z, xd.w);
+            tc_wait_ld(); release(b1); if (more) issue(b1 + 1, 0, dA, wA); compute(3, dB, wB, xd.z, xd.w);
         }
         // hsum_float_8 (LC/ggml.c:608-616): ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), then + summs
         if (m < B) {
@@ -264,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
 // quantize_act with the quants written as fp16 in plain row-major [B][K] (the TMA source), same arithmetic as quantize_act_kernel (quant.cu)
 template <bool Q81>
 __global__ void __launch_bounds__(256) quantize_act_f16_rm_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__ xh, float2 *__restrict__ ds,
-                                                                  int64_t nbk, int64_t total_blocks) {
+                                                                  int64_t nbk, int64_t total_blocks, int64_t rows) {
     const int64_t blk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (blk >= total_blocks) return;
     const int lane = threadIdx.x & 31;
@@ -276,7 +294,8 @@ __global__ void __launch_bounds__(256) quantize_act_f16_rm_kernel(const float *_
     const int q = __float2int_rn(__fmul_rn(v, id));
     const int isum = warp_sum(q);
     xh[(row * nbk + b) * QK + lane] = __int2half_rn(q);
-    if (lane == 0) ds[blk] = Q81 ? make_float2(d, __fmul_rn(d, (float)isum)) : make_float2(__half2float(__float2half_rn(d)), (float)isum);
+    // scales in block-pair-major order [K/64][B] x float4 {d, aux of block 2p | d, aux of block 2p+1}: the kernel's per-stage piece is contiguous
+    if (lane == 0) ds[((b >> 1) * rows + row) * 2 + (b & 1)] = Q81 ? make_float2(d, __fmul_rn(d, (float)isum)) : make_float2(__half2float(__float2half_rn(d)), (float)isum);
 }
 
 template <int TYPE>
@@ -285,7 +304,7 @@ void launch_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *ds
     if (!set) { B200_CHECK(cudaFuncSetAttribute(mm_exact_tc5_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); set = true; }
     const CUtensorMap tm = make_tmap_2d_f16_sw128(xh, (uint64_t)w.K, (uint64_t)B, (uint64_t)w.K * 2, TM);
     dim3 grid((unsigned)((w.N + TN - 1) / TN), (unsigned)((B + TM - 1) / TM));
-    mm_exact_tc5_kernel<TYPE><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, w, xds, dst, ldd, B, addend, lda);
+    mm_exact_tc5_kernel<TYPE><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, w, (const float4 *)xds, dst, ldd, B, addend, lda);
     B200_CHECK(cudaGetLastError());
 }
 
@@ -294,17 +313,17 @@ void launch_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *ds
 void quantize_act_f16_rm(int vdt, const float *x, int64_t ldx, __half *xh, float2 *ds, int64_t K, int64_t B, cudaStream_t st) {
     const int64_t nbk = K / QK, total = nbk * B;
     if (total == 0) return;
-    if (vdt == T_Q8_1) quantize_act_f16_rm_kernel<true><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total);
-    else               quantize_act_f16_rm_kernel<false><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total);
+    if (vdt == T_Q8_1) quantize_act_f16_rm_kernel<true><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total, B);
+    else               quantize_act_f16_rm_kernel<false><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(x, ldx, xh, ds, nbk, total, B);
     B200_CHECK(cudaGetLastError());
 }
 
 int exact_tc5_check_timeout() { return tc5::check_timeout("mm_exact_tc5_kernel"); }
 
-// xh = quantized activations as fp16, row-major [B][K] (quantize_act_f16_rm); xds = {d, aux} per (token, block)
+// xh = quantized activations as fp16, row-major [B][K]; xds = {d, aux} per (block, token) in the block-pair-major order of quantize_act_f16_rm
 void mul_mat_q_exact_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st) {
     if (w.N == 0 || B == 0) return;
-    B200_ASSERT(w.nb % 2 == 0 && ((uintptr_t)xh & 15) == 0);
+    B200_ASSERT(w.nb % 2 == 0 && ((uintptr_t)xh & 15) == 0 && ((uintptr_t)xds & 15) == 0);
     switch (w.type) {
         case T_Q4_0: launch_tc5<T_Q4_0>(w, xh, xds, dst, ldd, B, addend, lda, st); break;
         case T_Q4_1: launch_tc5<T_Q4_1>(w, xh, xds, dst, ldd, B, addend, lda, st); break;

@@ -46,6 +46,7 @@ void mul_mat_q_exact_mma(const QWeight &w, const __half *xh, const float2 *xds, 
 // ---- exact_tc5.cu : the same bit-exact batched mat-mul on tcgen05 tensor cores (TMA-staged activations, TMEM accumulators) ------------
 // xh = fp16 quants, plain row-major [B][K] (16-byte aligned; the TMA source); xds as above
 void quantize_act_f16_rm(int vdt, const float *x, int64_t ldx, __half *xh, float2 *ds, int64_t K, int64_t B, cudaStream_t st);
+bool prefill_gemm_tc5();         // session.cu: B200_PREFILL_GEMM != "mma" (the default)
 int exact_tc5_check_timeout();   // debugging aid of the op-level entry points: non-zero if a pipeline barrier of the kernel ever timed out
 void mul_mat_q_exact_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 

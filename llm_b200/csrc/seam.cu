@@ -171,8 +171,13 @@ void op_mul_mat(const ggml_tensor *src0, const ggml_tensor *src1, ggml_tensor *d
         const int64_t ldx = is_contiguous(src1) ? K : (int64_t)(src1->nb[1] / 4);
         if (B >= 16 && !R.fast) {                                       // prefill: bit-exact, block dots on tensor cores
             __half *xh = (__half *)R.op_arena.get((size_t)xh_bytes(K, B), st);
-            quantize_act_f16(vec_dot_type(src0->type), x, ldx, xh, xds, K, B, st);
-            mul_mat_q_exact_mma(w, xh, xds, d, N, B, nullptr, 0, st);
+            if (prefill_gemm_tc5() && B >= 96) {                        // tcgen05 / TMEM / TMA kernel (exact_tc5.cu)
+                quantize_act_f16_rm(vec_dot_type(src0->type), x, ldx, xh, xds, K, B, st);
+                mul_mat_q_exact_tc5(w, xh, xds, d, N, B, nullptr, 0, st);
+            } else {
+                quantize_act_f16(vec_dot_type(src0->type), x, ldx, xh, xds, K, B, st);
+                mul_mat_q_exact_mma(w, xh, xds, d, N, B, nullptr, 0, st);
+            }
             dst_finish(dst, d);
             return;
         }

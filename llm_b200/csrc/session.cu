@@ -121,6 +121,15 @@ namespace {
 struct Launches { int n = 0; };
 }  // namespace
 void silu_mul_rows(const float *h13, float *out, int64_t f, int64_t n, cudaStream_t st);
+// B200_PREFILL_GEMM=mma selects the round-1 mma.sync kernel for every batch size (default: tcgen05 for batches >= 96 tokens)
+namespace b200 {
+bool prefill_gemm_tc5() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("B200_PREFILL_GEMM"); v = (e && !strcmp(e, "mma")) ? 0 : 1; }
+    return v != 0;
+}
+}  // namespace b200
+
 namespace {
 
 // ggml_mul_mat(w, x): quantize the f32 activation rows (the INIT phase of ggml_compute_forward_mul_mat) and multiply
@@ -132,9 +141,14 @@ void matmul(b200_session *s, const QWeight &w, const float *x, float *dst, int64
         L.n += 2;
         return;
     }
-    if (!fast && B >= 16) {                          // prefill: bit-exact, block dots on tensor cores (exact_mma.cu)
-        quantize_act_f16(vec_dot_type(w.type), x, w.K, s->xh, s->xds, w.K, B, st);
-        mul_mat_q_exact_mma(w, s->xh, s->xds, dst, ldd, B, addend, lda, st);
+    if (!fast && B >= 16) {                          // prefill: bit-exact, block dots on tensor cores
+        if (prefill_gemm_tc5() && B >= 96) {         // tcgen05 / TMEM / TMA kernel: 128-token tiles (exact_tc5.cu)
+            quantize_act_f16_rm(vec_dot_type(w.type), x, w.K, s->xh, s->xds, w.K, B, st);
+            mul_mat_q_exact_tc5(w, s->xh, s->xds, dst, ldd, B, addend, lda, st);
+        } else {                                     // mma.sync kernel: 64-token tiles, better for short batches (exact_mma.cu)
+            quantize_act_f16(vec_dot_type(w.type), x, w.K, s->xh, s->xds, w.K, B, st);
+            mul_mat_q_exact_mma(w, s->xh, s->xds, dst, ldd, B, addend, lda, st);
+        }
         L.n += 2;
         return;
     }

@@ -147,6 +147,8 @@ class InferenceSession:
 
     def feed_prompt(self, tokens) -> np.ndarray:
         tokens = np.ascontiguousarray(tokens, np.int32)
+        if tokens.size == 0:                      # the reference leaves last_logits untouched for an empty prompt (inference_session.rs:299-350)
+            return self.last_logits
         out = np.empty(self.n_vocab, np.float32)
         _check(self.L.b200_session_feed_prompt(self._s, tokens.ctypes.data_as(C.c_void_p), tokens.size,
                                                out.ctypes.data_as(C.c_void_p)), "feed_prompt")

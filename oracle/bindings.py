@@ -55,6 +55,10 @@ class RefLib:
         L.rh_llama_tensor.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t)]
         L.rh_llama_finalize.argtypes = [C.c_void_p]
         L.rh_llama_reset.argtypes = [C.c_void_p]
+        for fn, at in (("rh_llama_set_n_past", [C.c_void_p, C.c_int]), ("rh_llama_set_threads", [C.c_void_p, C.c_int]),
+                       ("rh_llama_set_rope", [C.c_void_p, C.c_float, C.c_float])):
+            if hasattr(L, fn):                                          # a prebuilt oracle/_ref of an older recipe lacks them
+                getattr(L, fn).argtypes = at
         L.rh_llama_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.rh_llama_free.argtypes = [C.c_void_p]
         L.rh_llama_kv.restype = C.c_void_p
@@ -200,8 +204,10 @@ class RefLlama:
     def set_n_past(self, n):
         self.ref.lib.rh_llama_set_n_past(self.m, int(n))
 
+    def set_threads(self, n):
+        self.ref.lib.rh_llama_set_threads(self.m, int(n))
+
     def set_rope(self, freq_base, freq_scale):
-        self.ref.lib.rh_llama_set_rope.argtypes = [C.c_void_p, C.c_float, C.c_float]
         self.ref.lib.rh_llama_set_rope(self.m, freq_base, freq_scale)
 
     def kv_ptr(self, which):
@@ -213,6 +219,13 @@ class RefLlama:
     def eval(self, tokens):
         tokens = np.ascontiguousarray(tokens, np.int32)
         logits = np.empty((tokens.size, self.hp["n_vocab"]), np.float32)
+        rc = self.ref.lib.rh_llama_eval(self.m, _p(tokens), tokens.size, _p(logits), None)
+        assert rc == 0, rc
+        return logits
+
+    def eval_into(self, tokens, logits):
+        """same, into a caller-owned [n, n_vocab] f32 buffer (timing loops: no allocation per step)"""
+        tokens = np.ascontiguousarray(tokens, np.int32)
         rc = self.ref.lib.rh_llama_eval(self.m, _p(tokens), tokens.size, _p(logits), None)
         assert rc == 0, rc
         return logits
@@ -270,6 +283,8 @@ class Oracle:
         L.or_llama_tensor.restype = C.c_void_p
         L.or_llama_tensor.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t)]
         L.or_llama_reset.argtypes = [C.c_void_p]
+        L.or_llama_set_n_past.argtypes = [C.c_void_p, C.c_int]
+        L.or_llama_set_rope.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.or_llama_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.or_llama_kv.restype = C.c_void_p
         L.or_llama_kv.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
@@ -382,11 +397,9 @@ class OracleLlama:
         self.orc.lib.or_llama_reset(self.m)
 
     def set_n_past(self, n):
-        self.orc.lib.or_llama_set_n_past.argtypes = [C.c_void_p, C.c_int]
         self.orc.lib.or_llama_set_n_past(self.m, int(n))
 
     def set_rope(self, freq_base, freq_scale):
-        self.orc.lib.or_llama_set_rope.argtypes = [C.c_void_p, C.c_float, C.c_float]
         self.orc.lib.or_llama_set_rope(self.m, freq_base, freq_scale)
 
     def eval(self, tokens, tap_layer=None):

@@ -204,6 +204,8 @@ int rh_llama_finalize(rh_model *m) {
 void rh_llama_reset(rh_model *m) { m->n_past = 0; }
 /* session rewind / restore: continue from position n with whatever the KV cache holds (the bench's CPU arm installs the cache contents) */
 void rh_llama_set_n_past(rh_model *m, int n) { m->n_past = n; }
+/* InferenceSessionConfig::n_threads of the next evaluate (bench.py tries several counts on ONE loaded model) */
+void rh_llama_set_threads(rh_model *m, int n) { m->hp.n_threads = n; }
 /* RoPEOverrides -> op_rope_inplace takes the ggml_rope_custom_inplace branch (crates/ggml/src/context.rs:558-590) */
 void rh_llama_set_rope(rh_model *m, float freq_base, float freq_scale) { m->rope_custom = 1; m->rope_base = freq_base; m->rope_scale = freq_scale; }
 int  rh_llama_n_past(rh_model *m) { return m->n_past; }

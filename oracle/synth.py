@@ -61,6 +61,30 @@ def make_llama(hp, wtype, quantize, seed=0x5EED0000, gain=1.0):
     return hp, out
 
 
+def make_llama_random_blocks(hp, wtype, seed=0x5EED0000):
+    """A full-size model in seconds: the quantized blocks are drawn directly (uniform quants, fp16 scales ~ U[0.5, 1.5] * 2 / (15 sqrt(K)))
+    instead of quantizing 7e9 gaussians -- for TIMING the reference on the published configuration (bench.py --impl reference); parity
+    tests use make_llama or device-synthesised weights read back."""
+    hp = dict(hp, wtype=wtype)
+    rng = np.random.default_rng(seed)
+    bb = B.BLOCK_BYTES[wtype]
+    out = {}
+    for name, shp in tensor_shapes(hp).items():
+        if len(shp) == 1:
+            out[name] = (1.0 + 0.1 * rng.standard_normal(shp)).astype(np.float32)
+            continue
+        n, k = shp
+        nb = k // 32
+        blk = rng.integers(0, 256, size=(n, nb, bb), dtype=np.uint8)
+        d = ((rng.random((n, nb), dtype=np.float32) + 0.5) * np.float32(2.0 / (15.0 * np.sqrt(k)))).astype(np.float16)
+        blk[:, :, 0:2] = d.view(np.uint8).reshape(n, nb, 2)
+        if wtype in (B.Q4_1, B.Q5_1):              # {d, m}: a small finite min
+            m = (-rng.random((n, nb), dtype=np.float32) / np.float32(np.sqrt(k))).astype(np.float16)
+            blk[:, :, 2:4] = m.view(np.uint8).reshape(n, nb, 2)
+        out[name] = blk.reshape(n, nb * bb)
+    return hp, out
+
+
 def make_tokens(hp, n, seed=0x70CE11):
     return np.random.default_rng(seed).integers(0, hp["n_vocab"], size=n, dtype=np.int32)
 
