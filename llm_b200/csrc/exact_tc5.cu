@@ -39,6 +39,10 @@ constexpr int B_HALF = 16 * B_SBO;                                // one block-d
 constexpr int B_STAGE = 4 * B_HALF;                               // [block j][half h]
 constexpr int XR = NST + 2, X_STAGE = TM * 16;                    // ring of per-stage activation scales: [token] float4 {d, aux} x 2 blocks
 constexpr int NTHREADS = 384;
+// setmaxnreg re-splits the CTA's OWN register pool (what the launch allocated: 384 threads x 168, the __launch_bounds__(384, 1) cap); a split that asks
+// for more than the pool never completes (the kernel hangs in USETMAXREG.TRY_ALLOC)
+constexpr int PROD_REGS = 56, EPI_REGS = 224;
+static_assert(128 * PROD_REGS + 256 * EPI_REGS <= NTHREADS * 168, "register split exceeds the CTA's pool");
 constexpr int SMEM_BYTES = 1024 + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + XR * X_STAGE + 256;
 
 template <int TYPE> struct Tc {
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
     bool dead = false;
 
     if (warp < 4) {
-        reg_dealloc<64>();
+        reg_dealloc<PROD_REGS>();
         if (warp == 0) {
             // ================= TMA producer =================
             if (lane == 0) {
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
         // Software pipeline over "chunks" (4 rows = 2 x 16 TMEM columns): iteration g waits for the loads of chunk g (issued one iteration
         // earlier), issues the loads of chunk g + 1 -- tcgen05.ld and the rows' weight scales -- and only then runs the fp32 chain of chunk g,
         // so the TMEM / shared-memory latency hides behind 20 arithmetic instructions of the same warp (and the SM's other 7 epilogue warps).
-        reg_alloc<224>();
+        reg_alloc<EPI_REGS>();
         const int q = warp & 3, ch = (warp - 4) >> 2, tok = q * 32 + lane;
         const int64_t m = m_base + tok;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ch * 64;
