@@ -70,6 +70,11 @@ int  b200_init(int device);                                   /* accelerator::in
 int  b200_device_info(int32_t *sm_count, size_t *free_bytes, size_t *total_bytes);
 
 b200_model *b200_llama_new(const b200_llama_hparams *hp);
+/* Tensor-parallel shard tp_rank of tp_world (one process per GPU, <= 8; the north star's "weight rows shard across the 8 GPUs"): every 2-D weight but
+ * tok_embeddings holds only this rank's OUTPUT ROWS -- wq/wk/wv: its heads, w1/w3: rows [rank*n_ff/G, +n_ff/G), wo/w2: rows [rank*n_embd/G, +n_embd/G),
+ * output: rows [rank*n_vocab/G, +n_vocab/G) -- and b200_model_load_tensor takes exactly those rows.  Contrast: LC/ggml-cuda.cu:3355-3583 (row split by
+ * g_tensor_split + a gather per mat-mul).  Sessions of such a model decode one token per step (b200_session_evaluate loops over a batch). */
+b200_model *b200_llama_new_tp(const b200_llama_hparams *hp, int32_t tp_rank, int32_t tp_world);
 /* TensorLoader::load(name) + Tensor::transfer_to(Backend::Gpu): host bytes in GGML layout (block arrays for quantized types) */
 int  b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const void *host_data, size_t nbytes);
 /* fill every tensor with seeded synthetic weights generated ON the device (N(0,1/K) -> the reference's quantizer rule);
@@ -147,6 +152,12 @@ int64_t b200_session_read_tap(b200_session *s, float *host_out, int64_t max_coun
 /* kernels launched by the last evaluate (for bench.py's gpu_launches) and whether it replayed a CUDA graph */
 int32_t b200_session_last_launches(const b200_session *s);
 void b200_session_free(b200_session *s);
+/* Tensor-parallel sessions: each rank exports the CUDA IPC handle (64 bytes) of its exchange slab, the host layer gathers the handles of all ranks
+ * (any channel: torch.distributed, MPI, a pipe) and hands the table [tp_world][64] back; after that the decode kernels store their output slices
+ * straight into every peer's slab over NVLink (llm_b200/csrc/tp.cuh).  Every rank must call evaluate with the same tokens in the same order. */
+int  b200_session_tp_handle(b200_session *s, void *handle_out64);
+int  b200_session_tp_connect(b200_session *s, const void *handles_by_rank);
+int32_t b200_session_tp_timeouts(b200_session *s);
 
 /* stream handle (cudaStream_t) on which everything above is ordered -- for CUDA-event timing from the host side */
 void *b200_stream(void);

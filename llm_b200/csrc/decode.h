@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "tp.cuh"
 
 #ifndef B200_PROF_SLOTS
 #define B200_PROF_SLOTS 1024
@@ -30,6 +31,11 @@ struct DecodeParams {
     float *x, *q, *kq, *attn, *ff, *h13, *logits;
     int scratch_bytes;                  // decode_scratch_bytes(): per-CTA shared memory behind the weight ring
     int4 *xpack_d, *xpack_f;            // activation records produced by phase C (for wo) and phase E (for w2)
+    // tensor-parallel decode (tp.cuh): dims above are THIS RANK's (n_head, n_head_kv, gqa = local heads / cache width; f = local n_ff / G;
+    // n_vocab = local rows of the lm_head) except e = the full n_embd; e_loc = n_embd / G (q rows, rows of wo / w2 owned here)
+    TpCtx tp;
+    int e_loc = 0, head0 = 0;           // first global head of this rank
+    int64_t row0_e = 0, row0_w13 = 0, row0_v = 0;   // first row of this rank in the full wo / w2 output, the interleaved [w1|w3] rows, the lm_head
     unsigned int *bar;                  // [0] arrival count, [1] generation
     unsigned long long *prof;   /* graph schedule: 3 x B200_PROF_SLOTS timeline slots (begin | end | prologue done) */           // optional: %globaltimer stamps of CTA 0 at phase boundaries (debug / tuning), 128 slots
 };

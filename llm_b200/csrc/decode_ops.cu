@@ -21,6 +21,7 @@
 
 #include "decode.h"
 #include "stream_core.cuh"
+#include "tp.cuh"
 
 namespace b200 {
 
@@ -73,11 +74,12 @@ __device__ __forceinline__ float f16dot_tree(float s) {          // ggml_vec_dot
 // ---- 1 / 6: rms_norm * gain -> records.  grid = e/128 CTAs of 256 threads; every CTA reduces the whole row (16 KB from L2) and
 //      quantizes its own 4 blocks per warp pass. ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
-                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof) {
+                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpCtx T, const TpSync S) {
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
     pdl_wait();
+    if (T.world > 1) { if (tid == 0) tp_wait_thread(T, S); __syncthreads(); }     // tensor-parallel: every rank's slice of the row has landed
     prof_begin(prof);
     // this CTA's 32 blocks are float4s [blockIdx.x * 256, +256) of the row: thread tid packs float4 blockIdx.x * 256 + tid, which is also
     // one of the values it sums -- the row is read once, all loads (row and gains) are in flight before the first use (one L2 round trip)
@@ -125,6 +127,8 @@ struct MmvArgs {
     int nst;                      // ring depth chosen by launch_mmv
     int pdl_early;                // trigger the dependents from the producer warp once every byte is requested (B200_PDL_EARLY, default 1)
     unsigned long long *prof;
+    // tensor-parallel decode (tp.cuh): this rank owns rows [row0, row0 + w.N) of the full matrix; results go to buffer dst_buf of every rank
+    TpCtx tp; TpSync ts; int64_t row0; int dst_buf;
 };
 
 template <int TYPE, int EPI>
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         return;
     }
     pdl_wait();
+    if (A.tp.world > 1 && A.ts.wait_buf >= 0) { if (tid == 0) tp_wait_thread(A.tp, A.ts); compute_sync(); }   // the gathered input records are complete
     for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
     asm volatile("cp.async.wait_all;" ::: "memory");
     float *stash = (float *)(sx + (size_t)w.nb * 4);      // 64 floats behind the records (EPI_SILU)
@@ -153,7 +158,10 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
     const int lane = tid & 31, warp = tid >> 5;
     if (EPI == EPI_RES || EPI == EPI_LOGITS) {
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
-            if ((tid & 3) == 0 && row < w.N) A.dst[row] = A.addend ? __fadd_rn(v, __ldcg(A.addend + row)) : v;
+            if ((tid & 3) != 0 || row >= w.N) return;
+            const int64_t g = A.row0 + row;                      // row of the full matrix (row0 = 0 on a single GPU)
+            const float out = A.addend ? __fadd_rn(v, __ldcg(A.addend + g)) : v;
+            if (A.tp.world > 1) tp_store_f32(A.tp, A.dst_buf, g, out); else A.dst[g] = out;
         }, 1, A.prof);
         if (EPI == EPI_LOGITS && blockIdx.x == 0 && tid == 0) *A.n_past_inc = *A.n_past_inc + 1;
     } else if (EPI == EPI_QKV) {
@@ -184,11 +192,16 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
                 float4 hm;
                 hm.x = __fmul_rn(lutf(A.lut_silu, a.x), b.x); hm.y = __fmul_rn(lutf(A.lut_silu, a.y), b.y);
                 hm.z = __fmul_rn(lutf(A.lut_silu, a.z), b.z); hm.w = __fmul_rn(lutf(A.lut_silu, a.w), b.w);
-                pack_quad(hm, A.xpack_out + (row >> 6) * 4, lane, lane < 8, A.q81, A.off, A.scale16);
+                const int64_t blk = (A.row0 >> 6) + (row >> 6);     // block of w2's input (row0 counts this rank's interleaved w1|w3 rows)
+                int4 rec;
+                if (pack_quad_rec(hm, lane, lane < 8, A.q81, A.off, A.scale16, rec)) {
+                    if (A.tp.world > 1) tp_store_rec(A.tp, TPB_XF, blk * 4 + (lane & 7), rec); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
+                }
             }
             compute_sync();
         }, G, A.prof);
     }
+    if (A.tp.world > 1 && A.ts.sig_buf >= 0) { compute_sync(); if (tid == 0) tp_signal_thread(A.tp, A.ts, gridDim.x); }
     pdl_trigger();                                              // late: this CTA has consumed its last tile
     prof_end(A.prof);
 }
@@ -353,7 +366,7 @@ constexpr int ATH = 256;
 __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, const __half *__restrict__ Vl,
                                                          int4 *__restrict__ xpack_out, const int *__restrict__ n_past, const uint16_t *__restrict__ lut_exp,
                                                          float kq_scale, int hd, int n_head, int n_head_kv, int gqa, int n_ctx, int nlay, int q81, int off, int scale16,
-                                                         unsigned long long *prof) {
+                                                         unsigned long long *prof, const TpCtx T, const TpSync S, int head0) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) uint8_t sm[];
@@ -462,7 +475,14 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
         }
     }
     __syncthreads();
-    if (warp == 0) pack_quad(((const float4 *)stash)[lane & 7], xpack_out + (int64_t)((h * hd + c0) / QK) * 4, lane, lane < 8, q81, off, scale16);
+    if (warp == 0) {
+        int4 rec;
+        const int64_t blk = (int64_t)(((head0 + h) * hd + c0) / QK);       // block of wo's input: heads are global (head0 = first head of this rank)
+        if (pack_quad_rec(((const float4 *)stash)[lane & 7], lane, lane < 8, q81, off, scale16, rec)) {
+            if (T.world > 1) tp_store_rec(T, TPB_XD, blk * 4 + (lane & 7), rec); else xpack_out[blk * 4 + (lane & 7)] = rec;
+        }
+    }
+    if (T.world > 1) { __syncthreads(); if (tid == 0) tp_signal_thread(T, S, gridDim.x); }
     prof_end(prof);
 }
 
@@ -505,10 +525,22 @@ void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
     launch_k<1>(mmv_fused_kernel<TYPE, EPI>, dim3((unsigned)(groups < slots ? groups : slots)), dim3(STHREADS), (size_t)smem_of(nst), st, w, A);
 }
 
+// last node of a tensor-parallel token: every rank's logits slice has landed here; then the epoch moves on (tp.cuh)
+__global__ void tp_fence_kernel(const TpCtx T, const TpSync S) {
+    pdl_wait();
+    if (threadIdx.x == 0) { tp_wait_thread(T, S); __threadfence(); *T.epoch = *(volatile unsigned *)T.epoch + 1; }
+}
+
 template <int TYPE>
 void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers, int n_kv_bucket, int4 *xpack_a, cudaStream_t st, int *launches) {
     const int q81 = has_min(TYPE) ? 1 : 0, off = TYPE == T_Q5_0 ? 16 : 0, s16 = TYPE == T_Q4_0 ? 1 : 0;
     const int e = P.e, f = P.f;
+    const TpCtx &T = P.tp;
+    const bool tp = T.world > 1;
+    const int e_loc = tp ? P.e_loc : e;
+    auto ts = [&](int wait_buf, unsigned wait_v, int sig_buf, unsigned sig_v, int site) {
+        TpSync S; S.wait_buf = tp ? wait_buf : -1; S.wait_v = wait_v; S.sig_buf = tp ? sig_buf : -1; S.sig_v = sig_v; S.site = site; return S;
+    };
     int n = 0;
     auto pr = [&]() -> unsigned long long * { return P.prof && n < B200_PROF_SLOTS ? P.prof + n : nullptr; };   // timeline slot of the next launch
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
@@ -516,7 +548,8 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     static const bool fused_env = !(getenv("B200_ATTN_FUSED") && getenv("B200_ATTN_FUSED")[0] == '0');
     const int nlay = (n_kv_bucket + 63) / 64 * 64;
     const size_t fa_smem = (((size_t)nlay * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (nlay + 32) * 2;
-    const bool fused_attn = fused_env && P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024;
+    const bool fused_attn = (fused_env || tp) && P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024;
+    B200_ASSERT(fused_attn || !tp);                              // the tensor-parallel exchange lives in the fused attention kernel's epilogue
     static size_t fa_set = 48 * 1024;
     if (fused_attn && fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
     const size_t sv_smem = (size_t)P.n_ctx * 6 + 32 * KC * 2 + 32 * 32 * 2;
@@ -524,8 +557,10 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     if (sv_smem > sv_set) { B200_CHECK(cudaFuncSetAttribute(attn_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem)); sv_set = sv_smem; }
     for (int il = 0; il < P.n_layer; il++) {
         const DecodeLayer &L = layers[il];
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr()); n++;
-        MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e; A.gqa = P.gqa;
+        const unsigned v = (unsigned)il + 1;                     // flag value of this layer's exchanges (tp.cuh)
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T,
+                 ts(il > 0 ? TPB_X : -1, (unsigned)il, -1, 0, 0)); n++;                 // x of layer il-1 (every rank's rows of w2 h + inpFF)
+        MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e_loc; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
         A.prof = pr(); launch_mmv<TYPE, EPI_QKV>(L.wqkv, A, st); n++;
         if (fused_attn) {
@@ -538,7 +573,8 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
             at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
             B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
-                                          (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, nlay, q81, off, s16, pr()));
+                                          (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, nlay, q81, off, s16, pr(),
+                                          T, ts(-1, 0, TPB_XD, v, il * 4 + 0), tp ? P.head0 : 0));
             n++;
         } else {
             launch_k(P.hd == 128 ? attn_kq_kernel<128> : attn_kq_kernel<64>, dim3((n_kv_bucket + 63) / 64, P.n_head), dim3(128), 0, st,
@@ -548,16 +584,22 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
                      P.n_head_kv, P.n_ctx, q81, off, s16, pr()); n++;
         }
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;
+        Bo.tp = T; Bo.ts = ts(TPB_XD, v, TPB_FF, v, il * 4 + 1); Bo.row0 = tp ? P.row0_e : 0; Bo.dst_buf = TPB_FF;
         Bo.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.wo, Bo, st); n++;
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr()); n++;
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T, ts(TPB_FF, v, -1, 0, 0)); n++;
         MmvArgs C{}; C.xpack = xpack_a; C.xpack_out = P.xpack_f; C.lut_silu = P.lut_silu; C.q81 = q81; C.off = off; C.scale16 = s16;
+        C.tp = T; C.ts = ts(-1, 0, TPB_XF, v, il * 4 + 2); C.row0 = tp ? P.row0_w13 : 0;
         C.prof = pr(); launch_mmv<TYPE, EPI_SILU>(L.w13, C, st); n++;
         MmvArgs D{}; D.xpack = P.xpack_f; D.dst = P.x; D.addend = P.ff;
+        D.tp = T; D.ts = ts(TPB_XF, v, TPB_X, v, il * 4 + 3); D.row0 = tp ? P.row0_e : 0; D.dst_buf = TPB_X;
         D.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.w2, D, st); n++;
     }
-    launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr()); n++;
+    launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(), T,
+             ts(P.n_layer > 0 ? TPB_X : -1, (unsigned)P.n_layer, -1, 0, 0)); n++;
     MmvArgs Z{}; Z.xpack = xpack_a; Z.dst = P.logits; Z.addend = nullptr; Z.n_past_inc = P.n_past;
+    Z.tp = T; Z.ts = ts(-1, 0, TPB_LOGITS, 1, P.n_layer * 4); Z.row0 = tp ? P.row0_v : 0; Z.dst_buf = TPB_LOGITS;
     Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS>(P.output, Z, st); n++;
+    if (tp) { launch_k(tp_fence_kernel, dim3(1), dim3(32), 0, st, T, ts(TPB_LOGITS, 1, -1, 0, 0)); n++; }
     B200_CHECK(cudaGetLastError());
     (void)f;
     if (launches) *launches = n;

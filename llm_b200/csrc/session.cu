@@ -45,6 +45,9 @@ struct Layer {
 struct b200_model {
     b200_llama_hparams hp;
     int gqa = 0, hd = 0;
+    // tensor parallelism (b200_llama_new_tp): this rank holds 1/tp_world of the ROWS of every weight matrix (tp.cuh); *_loc = local row counts
+    int tp_rank = 0, tp_world = 1;
+    int e_loc = 0, gqa_loc = 0, f_loc = 0, v_loc = 0;
     char *slab = nullptr;               // one HBM allocation for every weight
     size_t slab_bytes = 0, weight_bytes = 0;
     QWeight wte, output;
@@ -90,10 +93,16 @@ struct b200_session {
     DecodeParams dp;
     int tap_layer = -2, tap_stage = 0;
     float *tap = nullptr; size_t tap_cap = 0, tap_count = 0;
+    // tensor parallelism: the exchange slab (x | ff | records | logits | flags), [epoch, timeouts, CTA-arrival counters], peers' slabs mapped through CUDA IPC
+    char *tp_slab = nullptr; size_t tp_slab_bytes = 0; unsigned *tp_state = nullptr;
+    void *tp_peer_map[TP_MAX] = {};
+    bool tp_connected = false;
 };
 
 bool b200_model::lookup(const char *name, Slot &s, int &slot_id) {
-    const int e = hp.n_embd, f = hp.n_ff;
+    const int e = hp.n_embd;
+    const int eq = e_loc, f = f_loc;          // local row counts (== n_embd, n_ff on a single GPU)
+    const int gqa = gqa_loc;
     s = Slot();
     if (!strcmp(name, "tok_embeddings.weight")) { s.q = wte; s.is_q = true; slot_id = 0; return true; }
     if (!strcmp(name, "norm.weight")) { s.f = norm; s.n = e; slot_id = 1; return true; }
@@ -105,9 +114,9 @@ bool b200_model::lookup(const char *name, Slot &s, int &slot_id) {
     if (!strcmp(sub, "attention_norm.weight")) { s.f = L.attention_norm; s.n = e; slot_id = base + 0; return true; }
     if (!strcmp(sub, "ffn_norm.weight"))       { s.f = L.ffn_norm; s.n = e; slot_id = base + 1; return true; }
     s.is_q = true;
-    if (!strcmp(sub, "attention.wq.weight")) { s.q = row_view(L.wqkv, 0, e); slot_id = base + 2; return true; }
-    if (!strcmp(sub, "attention.wk.weight")) { s.q = row_view(L.wqkv, e, gqa); slot_id = base + 3; return true; }
-    if (!strcmp(sub, "attention.wv.weight")) { s.q = row_view(L.wqkv, e + gqa, gqa); slot_id = base + 4; return true; }
+    if (!strcmp(sub, "attention.wq.weight")) { s.q = row_view(L.wqkv, 0, eq); slot_id = base + 2; return true; }
+    if (!strcmp(sub, "attention.wk.weight")) { s.q = row_view(L.wqkv, eq, gqa); slot_id = base + 3; return true; }
+    if (!strcmp(sub, "attention.wv.weight")) { s.q = row_view(L.wqkv, eq + gqa, gqa); slot_id = base + 4; return true; }
     if (!strcmp(sub, "attention.wo.weight")) { s.q = L.wo; slot_id = base + 5; return true; }
     if (!strcmp(sub, "feed_forward.w1.weight")) { s.q = L.w13; s.chunk = 32; s.row0 = 0;  s.stride = 64; s.rows = f; slot_id = base + 6; return true; }
     if (!strcmp(sub, "feed_forward.w3.weight")) { s.q = L.w13; s.chunk = 32; s.row0 = 32; s.stride = 64; s.rows = f; slot_id = base + 7; return true; }
@@ -172,14 +181,16 @@ void forward(b200_session *s, int n, bool all_rows = true) {
     const float kq_scale = 1.0f / sqrtf((float)e / (float)n_head);                           // llama lib.rs:268-270
     const RopeTable &rope = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, hd, n_ctx);
     Launches L;
-    const bool fast = (s->cfg.flags & B200_SESSION_FAST) != 0;
-    if (n == 1 && s->mega_ok && !fast && !(s->cfg.flags & B200_SESSION_UNFUSED) && s->tap_layer == -2) {
+    const bool tp = m->tp_world > 1;
+    const bool fast = !tp && (s->cfg.flags & B200_SESSION_FAST) != 0;
+    if (tp && (n != 1 || !s->tp_connected)) { fprintf(stderr, "llm_b200: tensor-parallel sessions decode one token per step, after b200_session_tp_connect\n"); exit(1); }
+    if (n == 1 && s->mega_ok && !fast && (tp || (!(s->cfg.flags & B200_SESSION_UNFUSED) && s->tap_layer == -2))) {
         if (s->dev_n_past != n_past) {                 // after a prefill / rewind the device copy of n_past is stale
             B200_CHECK(cudaStreamSynchronize(st));      // (the pinned staging word may still be in flight)
             *s->h_n_past = n_past;
             B200_CHECK(cudaMemcpyAsync(s->d_n_past, s->h_n_past, sizeof(int), cudaMemcpyHostToDevice, st));
         }
-        if (s->cfg.flags & B200_SESSION_MEGA) {
+        if (!tp && (s->cfg.flags & B200_SESSION_MEGA)) {
             // experimental: the whole token in one persistent cooperative kernel (decode.cu)
             if (launch_decode(s->dp, hp.wtype, st, &s->mega_grid)) {
                 s->dev_n_past = n_past + 1;
@@ -341,7 +352,7 @@ float b200_timing_end_ms(void) {
 }
 
 float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches, double *bytes) {
-    if (!s || reps < 1) return -1.f;
+    if (!s || reps < 1 || s->m->tp_world > 1) return -1.f;
     b200_model *m = s->m;
     cudaStream_t st = rt().stream;
     const int e = m->hp.n_embd, f = m->hp.n_ff;
@@ -372,17 +383,24 @@ float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches
     return ms;
 }
 
-b200_model *b200_llama_new(const b200_llama_hparams *hp) {
+static b200_model *llama_new_impl(const b200_llama_hparams *hp, int tp_rank, int tp_world) {
     if (!hp || !is_quant(hp->wtype) || hp->n_embd % 64 || hp->n_ff % 64 || hp->n_head <= 0 || hp->n_head_kv <= 0 ||
         hp->n_head % hp->n_head_kv || hp->n_embd % hp->n_head || hp->n_layer <= 0 || hp->context_size <= 0) return nullptr;
+    const int G = tp_world;
+    if (G < 1 || G > TP_MAX || tp_rank < 0 || tp_rank >= G) return nullptr;
+    const int gqa_full = hp->n_embd / (hp->n_head / hp->n_head_kv);
+    // row split: whole heads per rank, 32-row pieces of w1|w3 and of the lm_head, 32-element blocks of wo / w2's output slices
+    if (G > 1 && (hp->n_head % G || hp->n_head_kv % G || (hp->n_ff / G) % 32 || hp->n_ff % G || (hp->n_embd / G) % 32 || hp->n_vocab % G || (hp->n_vocab / G) % 32)) return nullptr;
     rt().ensure_init();
     b200_model *m = new b200_model();
     m->hp = *hp;
     if (m->hp.rope_freq_base == 0.f) m->hp.rope_freq_base = 10000.0f;
     if (m->hp.rope_freq_scale == 0.f) m->hp.rope_freq_scale = 1.0f;
-    const int e = hp->n_embd, f = hp->n_ff, v = hp->n_vocab, t = hp->wtype;
+    const int e = hp->n_embd, v = hp->n_vocab, t = hp->wtype;
     m->hd = e / hp->n_head;
-    m->gqa = e / (hp->n_head / hp->n_head_kv);
+    m->gqa = gqa_full;
+    m->tp_rank = tp_rank; m->tp_world = G;
+    m->e_loc = e / G; m->gqa_loc = gqa_full / G; m->f_loc = hp->n_ff / G; m->v_loc = v / G;
     m->layers.resize(hp->n_layer);
     // pass 1: sizes, pass 2: carve
     for (int pass = 0; pass < 2; pass++) {
@@ -393,10 +411,10 @@ b200_model *b200_llama_new(const b200_llama_hparams *hp) {
             if (pass) m->weight_bytes += (size_t)N * (K / QK) * ggml_block_bytes(t);
         };
         auto carve_f = [&](float *&p, int64_t n) { if (pass) p = (float *)(m->slab + off); off += ((size_t)n * 4 + 255) & ~(size_t)255; };
-        carve_q(m->wte, e, v); carve_q(m->output, e, v); carve_f(m->norm, e);
+        carve_q(m->wte, e, v); carve_q(m->output, e, m->v_loc); carve_f(m->norm, e);
         for (auto &L : m->layers) {
             carve_f(L.attention_norm, e); carve_f(L.ffn_norm, e);
-            carve_q(L.wqkv, e, e + 2 * m->gqa); carve_q(L.wo, e, e); carve_q(L.w13, e, 2 * f); carve_q(L.w2, f, e);
+            carve_q(L.wqkv, e, m->e_loc + 2 * m->gqa_loc); carve_q(L.wo, e, m->e_loc); carve_q(L.w13, e, 2 * m->f_loc); carve_q(L.w2, hp->n_ff, m->e_loc);
         }
         if (!pass) { m->slab_bytes = off; B200_CHECK(cudaMalloc(&m->slab, off)); }
     }
@@ -404,6 +422,13 @@ b200_model *b200_llama_new(const b200_llama_hparams *hp) {
     m->loaded.assign(m->n_slots(), 0);
     return m;
 }
+
+b200_model *b200_llama_new(const b200_llama_hparams *hp) { return llama_new_impl(hp, 0, 1); }
+
+// Tensor-parallel shard `tp_rank` of `tp_world` (one process per GPU): the model's tensors keep their names, but every 2-D weight except
+// tok_embeddings holds only this rank's rows -- wq / wk / wv: its heads; w1 / w3: rows [rank * n_ff/G, +n_ff/G); wo / w2: rows
+// [rank * n_embd/G, +n_embd/G); output: rows [rank * n_vocab/G, +n_vocab/G) -- and b200_model_load_tensor expects exactly those rows.
+b200_model *b200_llama_new_tp(const b200_llama_hparams *hp, int32_t tp_rank, int32_t tp_world) { return llama_new_impl(hp, tp_rank, tp_world); }
 
 size_t b200_model_weight_bytes(b200_model *m) { return m ? m->weight_bytes : 0; }
 
@@ -470,7 +495,7 @@ int b200_model_read_tensor(b200_model *m, const char *name, void *host_out, size
 }
 
 int b200_model_synthesize(b200_model *m, uint64_t seed) {
-    if (!m) return B200_ERR_BAD_ARG;
+    if (!m || m->tp_world > 1) return B200_ERR_BAD_ARG;       // shards are cut from a full model's tensors by the host (llm_b200/tp.py)
     cudaStream_t st = rt().stream;
     uint64_t id = 0;
     auto q = [&](const QWeight &w) { synth_qweight(w, seed + 0x1000003ull * (++id), st); };
@@ -492,11 +517,86 @@ void b200_model_free(b200_model *m) {
     delete m;
 }
 
+// ---- tensor-parallel session: decode only (prompts are fed token by token), activations that cross GPUs live in ONE exchange slab -------------
+static b200_session *start_session_tp(b200_session *s) {
+    b200_model *m = s->m;
+    const b200_llama_hparams &hp = m->hp;
+    const int G = m->tp_world, r = m->tp_rank;
+    const size_t e = hp.n_embd, f = hp.n_ff, n_ctx = hp.context_size, gqa = m->gqa_loc, V = hp.n_vocab;
+    s->cfg.n_batch = s->cfg.n_batch < 1 ? 1 : s->cfg.n_batch;
+    const size_t kv_elems = (size_t)hp.n_layer * n_ctx * gqa;
+    B200_CHECK(cudaMalloc(&s->memory_k, kv_elems * 2));
+    B200_CHECK(cudaMalloc(&s->memory_v, kv_elems * 2));
+    B200_CHECK(cudaMemset(s->memory_k, 0, kv_elems * 2));
+    B200_CHECK(cudaMemset(s->memory_v, 0, kv_elems * 2));
+    B200_CHECK(cudaMalloc(&s->d_tokens, (size_t)s->cfg.n_batch * 4));
+    B200_CHECK(cudaMallocHost(&s->h_tokens, (size_t)s->cfg.n_batch * 4));
+    B200_CHECK(cudaMallocHost(&s->h_logits, (size_t)s->cfg.n_batch * V * 4));
+    B200_CHECK(cudaMallocHost(&s->h_topk, 2048 * 4));
+    B200_CHECK(cudaMalloc(&s->topk, 2048 * 4));
+    B200_CHECK(cudaEventCreateWithFlags(&s->tokens_uploaded, cudaEventDisableTiming));
+    B200_CHECK(cudaMalloc(&s->qbuf, (size_t)m->e_loc * 4));
+    B200_CHECK(cudaMalloc(&s->xpack_a, (e / QK) * 64));
+    B200_CHECK(cudaMalloc(&s->d_n_past, sizeof(int)));
+    B200_CHECK(cudaMallocHost(&s->h_n_past, sizeof(int)));
+    B200_CHECK(cudaMalloc(&s->d_prof, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
+    B200_CHECK(cudaMemset(s->d_prof, 0, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
+    // the exchange slab: x | ff | attention records | ffn records | logits | flags, 256-byte aligned pieces
+    TpCtx &T = s->dp.tp;
+    T = TpCtx();
+    T.world = G; T.rank = r; T.vmul = (unsigned)hp.n_layer + 1;
+    size_t off = 0;
+    auto piece = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return (uint32_t)o; };
+    T.off[TPB_X] = piece(e * 4); T.off[TPB_FF] = piece(e * 4); T.off[TPB_XD] = piece((e / QK) * 64); T.off[TPB_XF] = piece((f / QK) * 64);
+    T.off[TPB_LOGITS] = piece(V * 4); T.off_flags = piece((size_t)TPB_COUNT * TP_MAX * 32);
+    s->tp_slab_bytes = off;
+    B200_CHECK(cudaMalloc(&s->tp_slab, off));
+    B200_CHECK(cudaMemset(s->tp_slab, 0, off));
+    B200_CHECK(cudaMalloc(&s->tp_state, (2 + (size_t)hp.n_layer * 4 + 1) * sizeof(unsigned)));
+    B200_CHECK(cudaMemset(s->tp_state, 0, (2 + (size_t)hp.n_layer * 4 + 1) * sizeof(unsigned)));
+    T.epoch = s->tp_state; T.arrivals = s->tp_state + 2;
+    for (int p = 0; p < TP_MAX; p++) T.peer[p] = nullptr;
+    T.peer[r] = s->tp_slab;                                              // peers are mapped by b200_session_tp_connect
+    s->x = (float *)(s->tp_slab + T.off[TPB_X]); s->ff = (float *)(s->tp_slab + T.off[TPB_FF]);
+    s->xpack_d = (int4 *)(s->tp_slab + T.off[TPB_XD]); s->xpack_f = (int4 *)(s->tp_slab + T.off[TPB_XF]);
+    s->logits = (float *)(s->tp_slab + T.off[TPB_LOGITS]);
+    const RopeTable &rt_ = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
+    {
+        std::vector<DecodeLayer> hl(hp.n_layer);
+        for (int il = 0; il < hp.n_layer; il++) {
+            const Layer &L = m->layers[il];
+            hl[il] = DecodeLayer{L.wqkv, L.wo, L.w13, L.w2, L.attention_norm, L.ffn_norm,
+                                 s->memory_k + (size_t)il * n_ctx * gqa, s->memory_v + (size_t)il * n_ctx * gqa};
+        }
+        s->h_layers = hl;
+    }
+    DecodeParams &P = s->dp;
+    P.layers = nullptr; P.n_layer = hp.n_layer; P.wte = m->wte; P.output = m->output; P.norm = m->norm;
+    P.e = (int)e; P.f = m->f_loc; P.hd = m->hd; P.gqa = m->gqa_loc; P.n_head = hp.n_head / G; P.n_head_kv = hp.n_head_kv / G; P.n_ctx = (int)n_ctx; P.n_vocab = m->v_loc;
+    P.kq_scale = 1.0f / sqrtf((float)hp.n_embd / (float)hp.n_head); P.eps = 5e-6f;
+    P.rope_cs = rt_.cs; P.rope_half = rt_.half;
+    P.lut_silu = luts().silu; P.lut_exp = luts().exp;
+    P.token = s->d_tokens; P.n_past = s->d_n_past;
+    P.x = s->x; P.q = s->qbuf; P.kq = nullptr; P.attn = nullptr; P.ff = s->ff; P.h13 = nullptr; P.logits = s->logits;
+    P.xpack_d = s->xpack_d; P.xpack_f = s->xpack_f; P.bar = nullptr; P.scratch_bytes = 0;
+    P.e_loc = m->e_loc; P.head0 = r * (hp.n_head / G);
+    P.row0_e = (int64_t)r * m->e_loc; P.row0_w13 = (int64_t)r * 2 * m->f_loc; P.row0_v = (int64_t)r * m->v_loc;
+    P.prof = nullptr;
+    QWeight probe; probe.nb = (int64_t)e / QK;
+    QWeight probe2; probe2.nb = (int64_t)f / QK;
+    s->mega_ok = hp.n_rot == m->hd && (m->hd == 64 || m->hd == 128) && mmv_exact_stream_supported(probe) && mmv_exact_stream_supported(probe2) &&
+                 m->gqa_loc % 32 == 0 && m->e_loc % 32 == 0 && hp.context_size % 8 == 0;
+    B200_CHECK(cudaDeviceSynchronize());
+    if (!s->mega_ok) { fprintf(stderr, "llm_b200: tensor-parallel session: geometry not supported by the fused decode schedule\n"); b200_session_free(s); return nullptr; }
+    return s;
+}
+
 b200_session *b200_model_start_session(b200_model *m, const b200_session_config *cfg) {
     if (!m || !cfg || cfg->n_batch < 1) return nullptr;
     if (m->n_loaded != m->n_slots()) { fprintf(stderr, "llm_b200: start_session: %d of %d tensors loaded\n", m->n_loaded, m->n_slots()); return nullptr; }
     b200_session *s = new b200_session();
     s->m = m; s->cfg = *cfg;
+    if (m->tp_world > 1) return start_session_tp(s);
     const b200_llama_hparams &hp = m->hp;
     const size_t e = hp.n_embd, f = hp.n_ff, B = cfg->n_batch, n_ctx = hp.context_size, gqa = m->gqa;
     const size_t kv_elems = (size_t)hp.n_layer * n_ctx * gqa;
@@ -585,6 +685,15 @@ const float *b200_session_device_logits(b200_session *s) { return s ? s->logits 
 int b200_session_evaluate(b200_session *s, const int32_t *tokens, int32_t n, float *logits_out, int32_t all_logits) {
     if (!s || !tokens || n < 1 || n > s->cfg.n_batch) return B200_ERR_BAD_ARG;
     if (s->n_past + n > s->m->hp.context_size) return B200_ERR_CONTEXT_FULL;
+    if (s->m->tp_world > 1 && n > 1) {                  // tensor-parallel sessions have the decode schedule only: a batch is fed token by token
+        const size_t V = s->m->hp.n_vocab;
+        for (int i = 0; i < n; i++) {
+            float *out = !logits_out ? nullptr : all_logits ? logits_out + (size_t)i * V : (i == n - 1 ? logits_out : nullptr);
+            const int rc = b200_session_evaluate(s, tokens + i, 1, out, 0);
+            if (rc != B200_OK) return rc;
+        }
+        return B200_OK;
+    }
     for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= s->m->hp.n_vocab) return B200_ERR_BAD_ARG;
     cudaStream_t st = rt().stream;
     B200_CHECK(cudaEventSynchronize(s->tokens_uploaded));       // the previous (feed-only) call may still be reading the staging buffer
@@ -634,7 +743,7 @@ int b200_session_feed_prompt(b200_session *s, const int32_t *tokens, int32_t n, 
 
 int b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t nbytes) {
     if (!s || !host_out) return B200_ERR_BAD_ARG;
-    const size_t kv_bytes = (size_t)s->m->hp.n_layer * s->m->hp.context_size * s->m->gqa * 2;
+    const size_t kv_bytes = (size_t)s->m->hp.n_layer * s->m->hp.context_size * (s->m->tp_world > 1 ? s->m->gqa_loc : s->m->gqa) * 2;   // tensor-parallel: this rank's heads
     if (nbytes != kv_bytes) return B200_ERR_TENSOR_SHAPE;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     B200_CHECK(cudaMemcpy(host_out, which ? s->memory_v : s->memory_k, kv_bytes, cudaMemcpyDeviceToHost));
@@ -642,7 +751,7 @@ int b200_session_read_kv(b200_session *s, int32_t which, void *host_out, size_t 
 }
 
 int b200_session_set_tap(b200_session *s, int32_t layer, int32_t stage) {
-    if (!s) return B200_ERR_BAD_ARG;
+    if (!s || s->m->tp_world > 1) return B200_ERR_BAD_ARG;
     s->tap_layer = layer; s->tap_stage = stage; s->tap_count = 0;
     return B200_OK;
 }
@@ -681,11 +790,49 @@ int b200_session_decode_timeline(b200_session *s, unsigned long long *out, int n
 
 int b200_session_sync(b200_session *s) { (void)s; B200_CHECK(cudaStreamSynchronize(rt().stream)); return B200_OK; }
 
+// ---- tensor-parallel plumbing: exchange-slab handles (CUDA IPC; one process per GPU, handles travel over the host's own channel) --------
+int b200_session_tp_handle(b200_session *s, void *handle_out64) {
+    if (!s || !s->tp_slab || !handle_out64) return B200_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    B200_CHECK(cudaIpcGetMemHandle(&h, s->tp_slab));
+    memcpy(handle_out64, &h, 64);
+    return B200_OK;
+}
+int b200_session_tp_connect(b200_session *s, const void *handles_by_rank) {
+    if (!s || !s->tp_slab || !handles_by_rank) return B200_ERR_BAD_ARG;
+    TpCtx &T = s->dp.tp;
+    for (int p = 0; p < T.world; p++) {
+        if (p == T.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles_by_rank + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        const cudaError_t err = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) { fprintf(stderr, "llm_b200: cudaIpcOpenMemHandle(rank %d): %s\n", p, cudaGetErrorString(err)); return B200_ERR_IO; }
+        s->tp_peer_map[p] = ptr;
+        T.peer[p] = (char *)ptr;
+    }
+    s->tp_connected = true;
+    return B200_OK;
+}
+int32_t b200_session_tp_timeouts(b200_session *s) {      // number of flag waits that gave up (a peer stopped): must be 0
+    if (!s || !s->tp_state) return -1;
+    unsigned v[2] = {0, 0};
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    B200_CHECK(cudaMemcpy(v, s->tp_state, sizeof(v), cudaMemcpyDeviceToHost));
+    return (int32_t)v[1];
+}
+
 void b200_session_free(b200_session *s) {
     if (!s) return;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     if (s->h_n_past) B200_CHECK(cudaFreeHost(s->h_n_past));
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
+    if (s->tp_slab) {                                    // tensor-parallel session: x, ff, records and logits live inside the slab
+        for (int p = 0; p < TP_MAX; p++) if (s->tp_peer_map[p]) cudaIpcCloseMemHandle(s->tp_peer_map[p]);
+        B200_CHECK(cudaFree(s->tp_slab)); B200_CHECK(cudaFree(s->tp_state));
+        s->x = s->ff = s->logits = nullptr; s->xpack_d = s->xpack_f = nullptr;
+    }
     void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack, s->xh, s->topk};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));
     if (s->h_tokens) B200_CHECK(cudaFreeHost(s->h_tokens));

@@ -215,7 +215,8 @@ __device__ __forceinline__ void pack_block(float v, int4 *rec4, int lane, int q8
 // Same arithmetic, 4 blocks per warp pass: lane l owns word (l & 7) = elements 4*(l&7) .. +3 of block (l >> 3).  The block maximum and
 // the quant sum need 3 xor-shuffles each inside the 8-lane group, the packed word and its byte sum are lane-local, and the record's
 // second word comes from 4 lanes up: 8 shuffles per 4 blocks instead of 16 per block.  `active` = this lane's block exists.
-__device__ __forceinline__ void pack_quad(float4 v, int4 *rec4_of_my_block, int lane, bool active, int q81, int off, int scale16) {
+// returns true in the lanes that hold a record (word lane & 7 < 4 of an existing block); the caller stores it at [block * 4 + (lane & 7)]
+__device__ __forceinline__ bool pack_quad_rec(float4 v, int lane, bool active, int q81, int off, int scale16, int4 &rec) {
     float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
@@ -231,17 +232,18 @@ __device__ __forceinline__ void pack_quad(float4 v, int4 *rec4_of_my_block, int 
     isum += __shfl_xor_sync(0xffffffffu, isum, 4);
     const uint32_t word_hi = __shfl_down_sync(0xffffffffu, word, 4);
     const int s4_hi = __shfl_down_sync(0xffffffffu, s4, 4);
-    if (active && (lane & 7) < 4) {
-        int4 rec;
-        rec.x = (int)word; rec.y = (int)word_hi;
-        if (q81) { rec.z = __float_as_int(__fmul_rn(d, (float)isum)); rec.w = __float_as_int(d); }
-        else {
-            rec.z = (int)(((uint32_t)(-off * s4) & 0xffffu) | ((uint32_t)(-off * s4_hi) << 16));
-            const float dx = __half2float(__float2half_rn(d));
-            rec.w = __float_as_int(scale16 ? dx * 0.0625f : dx);
-        }
-        rec4_of_my_block[lane & 7] = rec;
+    rec.x = (int)word; rec.y = (int)word_hi;
+    if (q81) { rec.z = __float_as_int(__fmul_rn(d, (float)isum)); rec.w = __float_as_int(d); }
+    else {
+        rec.z = (int)(((uint32_t)(-off * s4) & 0xffffu) | ((uint32_t)(-off * s4_hi) << 16));
+        const float dx = __half2float(__float2half_rn(d));
+        rec.w = __float_as_int(scale16 ? dx * 0.0625f : dx);
     }
+    return active && (lane & 7) < 4;
+}
+__device__ __forceinline__ void pack_quad(float4 v, int4 *rec4_of_my_block, int lane, bool active, int q81, int off, int scale16) {
+    int4 rec;
+    if (pack_quad_rec(v, lane, active, q81, off, scale16, rec)) rec4_of_my_block[lane & 7] = rec;
 }
 
 }  // namespace stream
