@@ -43,6 +43,12 @@ def lib():
     L.b200_stream.restype = vp
     L.b200_llama_new.restype = vp
     L.b200_llama_new.argtypes = [C.POINTER(LlamaHparams)]
+    L.b200_llama_new_tp.restype = vp
+    L.b200_llama_new_tp.argtypes = [C.POINTER(LlamaHparams), i32, i32]
+    L.b200_session_tp_handle.argtypes = [vp, vp]
+    L.b200_session_tp_connect.argtypes = [vp, C.c_char_p]
+    L.b200_session_tp_timeouts.restype = i32
+    L.b200_session_tp_timeouts.argtypes = [vp]
     L.b200_model_load_tensor.argtypes = [vp, C.c_char_p, i32, vp, sz]
     L.b200_model_synthesize.argtypes = [vp, C.c_uint64]
     L.b200_model_read_tensor.argtypes = [vp, C.c_char_p, vp, sz]
