@@ -200,6 +200,146 @@ def cpu_reference(metric, steps, warmup, log=lambda *a: None, weights=None, gpu=
     return out
 
 
+MODELS = {"7b-q4_0": dict(HP_7B), "13b-q5_1": dict(n_vocab=32000, n_embd=5120, n_head=40, n_head_kv=40, n_layer=40, n_rot=128, n_ff=13824, wtype=7)}
+BLK_BYTES = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
+
+
+def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
+    """decode@1 at n_past = 512 of ONE model sharded by output rows over the N GPUs (strong scaling): every rank streams 1/N of the weights and its
+    heads' KV cache; activation slices cross NVLink as peer stores issued by the producing kernels' epilogues + release/acquire flags
+    (llm_b200/csrc/tp.cuh) -- torch.distributed (NCCL) only brackets the timed region and takes the max over ranks."""
+    import llm_b200
+    from llm_b200 import _lib, tp
+    from llm_b200.session import llama_tensor_shapes
+    L = _lib.lib()
+    hp = dict(MODELS[args.model])
+    if args.layers != 32:
+        hp["n_layer"] = args.layers
+    name = "LLaMA-7B Q4_0" if args.model == "7b-q4_0" else "LLaMA-13B Q5_1"
+    if world > 1:
+        rank, local_rank, world, dist = tp.init_distributed()
+    else:
+        dist = None
+    t0 = time.time()
+    # identical weights on every rank: synthesize the FULL model on this rank's GPU (same seed), cut this rank's rows, drop the full model
+    full = llm_b200.Llama(hp, llm_b200.ModelParameters(context_size=2048), device=local_rank)
+    full.synthesize(0x5EED0000)
+    if world > 1:
+        model = tp.TpLlama(hp, llm_b200.ModelParameters(context_size=2048), None, rank=rank, world=world, device=local_rank)
+        shapes = llama_tensor_shapes(hp)
+        for k in shapes:
+            v = full.read_tensor(k)
+            rows = tp.shard_rows(k, hp, rank, world)
+            if v.dtype == np.uint8:
+                v = v.reshape(shapes[k][0], -1)
+            model.load_tensor(k, v if rows is None else np.ascontiguousarray(v[rows[0]:rows[1]]))
+        full.close()
+        sess = model.start_session(llm_b200.InferenceSessionConfig(n_batch=8), dist)
+    else:
+        model = full
+        sess = model.start_session(llm_b200.InferenceSessionConfig(n_batch=512))
+    log(f"{name}: shard {rank}/{world} ready in {time.time() - t0:.1f}s; weight bytes streamed per token on this rank = {model.weight_bytes}")
+    prompt = np.random.default_rng(0x70CE11).integers(0, hp["n_vocab"], N_PAST + 1, dtype=np.int32)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        sess.sync()
+
+    def allmax(*vals):
+        if dist is None:
+            return vals
+        import torch
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t)
+
+    t0 = time.time()
+    if world > 1:                                                 # the tensor-parallel session has the decode schedule only: feed the prompt token by token
+        for i in range(N_PAST):
+            assert L.b200_session_evaluate(sess._s, prompt[i:i + 1].ctypes.data, 1, None, 0) == 0
+    else:
+        tok = np.ascontiguousarray(prompt[:N_PAST])
+        assert L.b200_session_evaluate(sess._s, tok.ctypes.data, N_PAST, None, 0) == 0
+    sess.sync()
+    log(f"KV cache filled to n_past={N_PAST} in {time.time() - t0:.1f}s")
+    one = np.ascontiguousarray(prompt[N_PAST:N_PAST + 1])
+    logits = np.empty(hp["n_vocab"], np.float32)
+    assert L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0) == 0
+    launches_per_step = sess.last_launches
+
+    def timed(n):
+        for _ in range(warmup):
+            sess.rewind(N_PAST); assert L.b200_session_evaluate_device(sess._s, None, 1) == 0
+        barrier()
+        L.b200_timing_begin()
+        for _ in range(n):
+            sess.rewind(N_PAST); L.b200_session_evaluate_device(sess._s, None, 1)
+        ms = L.b200_timing_end_ms()
+        barrier()
+        return ms
+
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(steps)
+        for _ in range(3):
+            sess.rewind(N_PAST); L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0)
+        barrier()
+        t0 = time.perf_counter()
+        L.b200_timing_begin()
+        for _ in range(steps):
+            sess.rewind(N_PAST); L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0)
+        ms_e2e = max(L.b200_timing_end_ms(), (time.perf_counter() - t0) * 1e3)
+        barrier()
+    clocks = clk.summary()
+    assert np.isfinite(logits).all()
+    ms_nowait = None
+    if world > 1:                                                 # the same schedule without the flag waits: what the exchange costs beyond compute + stores
+        assert L.b200_session_tp_set_nowait(sess._s, 1) == 0
+        ms_nowait = timed(steps)
+        assert L.b200_session_tp_set_nowait(sess._s, 0) == 0
+        assert sess.timeouts == 0, "a tensor-parallel flag wait timed out"
+    vals = allmax(ms_dev, ms_e2e, ms_nowait if ms_nowait is not None else 0.0)
+    ms_dev, ms_e2e = vals[0], vals[1]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    blk = BLK_BYTES[hp["wtype"]]
+    wbytes, kvbytes, embbytes = algorithmic_bytes_per_token(hp, N_PAST, blk)
+    tok_bytes = wbytes + kvbytes + embbytes
+    e, f = hp["n_embd"], hp["n_ff"]
+    exch = hp["n_layer"] * (2 * e * 4 + (e // 32) * 64 + (f // 32) * 64) + hp["n_vocab"] * 4      # bytes every rank ends up holding per token
+    line = {
+        "metric": f"{name} tokens/sec (decode@1, n_past=512)" if args.model != "7b-q4_0" else METRIC,
+        "value": steps / (ms_dev * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8/s8 block dots -> f32", "data": "synthetic",
+        "config": {"workload": f"{name} decode batch=1 n_past=512, ONE sequence on {world} GPU(s)" + (" (BASELINE.json configs[3])" if args.model == "13b-q5_1" else " (BASELINE.json configs[1])"),
+                   "n_layer": hp["n_layer"], "n_ctx": 2048, "kv_cache": "f16",
+                   "parallelism": (f"tp{world}: every weight matrix split by output rows (heads / n_ff / n_embd / n_vocab slices), bit-exact; activation slices are stored into every "
+                                   f"peer's buffers over NVLink by the producing epilogues + release/acquire flags; no NCCL on the data path") if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: weights streamed from HBM every step",
+                   "weights": "random-init, generated on device, identical on every rank (same seed), each rank keeps its rows"},
+        "e2e": {"value": steps / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * hp["n_vocab"] * world, "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches_per_step * steps * world, "launches_per_step": launches_per_step,
+        "roofline": None,
+        "step_roofline": {"bound": "hbm", "bytes_per_token": tok_bytes, "bytes_per_token_per_gpu": tok_bytes / world, "achieved_gbs": tok_bytes / (ms_dev / steps * 1e-3) / 1e9,
+                          "peak": pk["hbm_gbs"] * world, "frac": tok_bytes / (ms_dev / steps * 1e-3) / 1e9 / (pk["hbm_gbs"] * world), "unit": "GB/s (all GPUs)"},
+        "clocks": clocks,
+        "conformance": "row split keeps every dst element one complete vec_dot: logits bit-identical to the CPU oracle (tests/test_gpu_tp.py)",
+    }
+    if world > 1:
+        line["exchange"] = {"per_token": 4 * hp["n_layer"] + 1, "gathered_bytes_per_token_per_gpu": exch, "nvlink_bytes_per_token_per_gpu_sent": exch * (world - 1) // world,
+                            "ms_per_step_without_flag_waits": vals[2] / steps, "exposed_wait_share_of_step": max(0.0, 1.0 - vals[2] / ms_dev),
+                            "note": "time with the flag waits skipped (garbage results) = compute + peer stores; the difference is what waiting for the slowest rank's slices costs"}
+    emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +349,8 @@ def main():
     ap.add_argument("--metric", default="decode", choices=["decode", "prefill"], help="which half of BASELINE.json's metric the JSON line reports")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is NOT the benchmark config")
+    ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"], help="N > 1: tensor-parallel row split of ONE model (strong scaling, default) or N independent replicas")
+    ap.add_argument("--model", default="7b-q4_0", choices=["7b-q4_0", "13b-q5_1"], help="13b-q5_1 = BASELINE.json configs[3] (tensor-parallel decode only)")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON); libraries that print to fd 1 (e.g. NCCL's version banner) are sent to stderr
     sys.stdout.flush()
@@ -245,6 +387,8 @@ def main():
         return
 
     # ---- our arm ----------------------------------------------------------------------------------------------------
+    if (world > 1 and args.parallel == "tp") or args.model != "7b-q4_0":
+        return tp_main(args, rank, local_rank, world, steps, warmup, emit, log)
     dist = None
     if world > 1:
         import torch
@@ -422,10 +566,10 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         try:
             # the SAME model on the CPU: device-synthesised weights read back in GGML layout, the session's KV cache installed, one step compared
-            from oracle import synth
+            from llm_b200.session import llama_tensor_shapes
             t0 = time.time()
             weights = {}
-            for k, shp in synth.tensor_shapes(hp).items():
+            for k, shp in llama_tensor_shapes(hp).items():
                 v = model.read_tensor(k)
                 weights[k] = v.reshape(shp[0], -1) if v.dtype == np.uint8 else v
             sess.rewind(N_PAST)

@@ -47,6 +47,7 @@ def lib():
     L.b200_llama_new_tp.argtypes = [C.POINTER(LlamaHparams), i32, i32]
     L.b200_session_tp_handle.argtypes = [vp, vp]
     L.b200_session_tp_connect.argtypes = [vp, C.c_char_p]
+    L.b200_session_tp_set_nowait.argtypes = [vp, i32]
     L.b200_session_tp_timeouts.restype = i32
     L.b200_session_tp_timeouts.argtypes = [vp]
     L.b200_model_load_tensor.argtypes = [vp, C.c_char_p, i32, vp, sz]

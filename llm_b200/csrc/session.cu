@@ -815,6 +815,14 @@ int b200_session_tp_connect(b200_session *s, const void *handles_by_rank) {
     s->tp_connected = true;
     return B200_OK;
 }
+int b200_session_tp_set_nowait(b200_session *s, int32_t nowait) {     // measurement aid: the captured graphs carry the flag, so they are dropped
+    if (!s || !s->tp_slab) return B200_ERR_BAD_ARG;
+    B200_CHECK(cudaStreamSynchronize(rt().stream));
+    s->dp.tp.nowait = nowait ? 1 : 0;
+    for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
+    s->graphs.clear();
+    return B200_OK;
+}
 int32_t b200_session_tp_timeouts(b200_session *s) {      // number of flag waits that gave up (a peer stopped): must be 0
     if (!s || !s->tp_state) return -1;
     unsigned v[2] = {0, 0};

@@ -29,6 +29,7 @@ struct TpCtx {                 // kernel argument (POD); world == 1: single GPU,
     uint32_t off[TPB_COUNT] = {};  // byte offsets of the buffers inside a slab
     uint32_t off_flags = 0;        // [TPB_COUNT][TP_MAX] flags, 32 bytes apart
     unsigned vmul = 1;             // n_layer + 1
+    int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): skip the flag waits -- results are garbage, the time is compute + stores only
 };
 
 // what one kernel instance waits for / signals (baked into the CUDA graph; the epoch is read from device memory)
@@ -52,7 +53,7 @@ __device__ __forceinline__ void tp_store_rec(const TpCtx &T, int buf, int64_t id
 
 // one thread: spin until every rank's slice of `buf` for this (token, layer) has landed here
 __device__ __forceinline__ void tp_wait_thread(const TpCtx &T, const TpSync &S) {
-    if (T.world <= 1 || S.wait_buf < 0) return;
+    if (T.world <= 1 || S.wait_buf < 0 || T.nowait) return;
     const unsigned want = *(volatile unsigned *)T.epoch * T.vmul + S.wait_v;
     for (int src = 0; src < T.world; src++) {
         const unsigned *f = tp_flag(T, T.rank, S.wait_buf, src);

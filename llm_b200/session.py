@@ -44,6 +44,20 @@ class OutputRequest:
 _HP_KEYS = ("n_vocab", "n_embd", "n_head", "n_head_kv", "n_layer", "n_rot", "n_ff")
 
 
+def llama_tensor_shapes(hp: Dict[str, int]) -> Dict[str, tuple]:
+    """tensor name -> (rows N, cols K) for 2-D weights, (n,) for norm gains: the names the reference's loader asks for
+    (crates/models/llama/src/lib.rs:52-91)"""
+    e, f, v = hp["n_embd"], hp["n_ff"], hp["n_vocab"]
+    gqa = e // (hp["n_head"] // hp["n_head_kv"])
+    shapes = {"tok_embeddings.weight": (v, e), "norm.weight": (e,), "output.weight": (v, e)}
+    for i in range(hp["n_layer"]):
+        p = f"layers.{i}."
+        shapes.update({p + "attention_norm.weight": (e,), p + "attention.wq.weight": (e, e), p + "attention.wk.weight": (gqa, e),
+                       p + "attention.wv.weight": (gqa, e), p + "attention.wo.weight": (e, e), p + "ffn_norm.weight": (e,),
+                       p + "feed_forward.w1.weight": (f, e), p + "feed_forward.w2.weight": (e, f), p + "feed_forward.w3.weight": (f, e)})
+    return shapes
+
+
 def _check(rc, what):
     if rc == -1:
         raise ContextFull(what)
