@@ -171,6 +171,28 @@ float b200_timing_end_ms(void);
  * events.  Returns total ms; *launches = kernels launched, *bytes = algorithmic weight bytes streamed (all reps). */
 float b200_session_probe_matvec(b200_session *s, int32_t reps, int64_t *launches, double *bytes);
 
+/* ---- GPT-NeoX (crates/models/gptneox): KnownModel + InferenceSession, same conventions as the LLaMA entry points above --------------------------
+ * Hyperparameters (gptneox lib.rs:403-447 region): tensor names are the loader's ("gpt_neox.embed_in.weight", "gpt_neox.layers.N.attention.
+ * query_key_value.weight" [3e x e, rows per head: q | k | v], ..., "embed_out.weight"); every 2-D ".weight" is quantized to wtype, biases / LayerNorm f32. */
+typedef struct b200_neox_hparams {
+    int32_t n_vocab, n_embd, n_head, n_layer, n_rot, use_parallel_residual, wtype, context_size;
+} b200_neox_hparams;
+typedef struct b200_neox_model b200_neox_model;
+typedef struct b200_neox_session b200_neox_session;
+b200_neox_model *b200_neox_new(const b200_neox_hparams *hp);
+int  b200_neox_load_tensor(b200_neox_model *m, const char *name, int32_t type, const void *host_data, size_t nbytes);
+int  b200_neox_synthesize(b200_neox_model *m, uint64_t seed);          /* seeded weights generated in HBM (bench) */
+size_t b200_neox_weight_bytes(b200_neox_model *m);                     /* bytes streamed per decoded token */
+void b200_neox_free(b200_neox_model *m);
+b200_neox_session *b200_neox_start_session(b200_neox_model *m, int32_t n_batch);
+int  b200_neox_evaluate(b200_neox_session *s, const int32_t *tokens, int32_t n, float *logits_out, int32_t all_logits);
+int  b200_neox_evaluate_device(b200_neox_session *s, int32_t n);       /* tokens of the last evaluate stay in HBM, logits stay in HBM */
+int32_t b200_neox_n_past(const b200_neox_session *s);
+int  b200_neox_set_n_past(b200_neox_session *s, int32_t n_past);
+int32_t b200_neox_last_launches(const b200_neox_session *s);
+int  b200_neox_sync(b200_neox_session *s);
+void b200_neox_session_free(b200_neox_session *s);
+
 /* ---- single-op entry points on HOST buffers (unit tests, INTEGRATION examples).  Each uploads, runs the kernel, downloads. */
 int  b200_op_quantize_act(int32_t vec_dot_type, const float *x, int64_t K, int64_t B, int8_t *qs_out, float *d_out, float *aux_out);
 int  b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, const float *x, int64_t B, float *dst, int32_t impl);

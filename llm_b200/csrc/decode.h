@@ -40,6 +40,25 @@ struct DecodeParams {
     unsigned long long *prof;   /* graph schedule: 3 x B200_PROF_SLOTS timeline slots (begin | end | prologue done) */           // optional: %globaltimer stamps of CTA 0 at phase boundaries (debug / tuning), 128 slots
 };
 
+// ---- GPT-NeoX (crates/models/gptneox/src/lib.rs:156-350) fused decode schedule: 8 kernels per layer, same mat-vec core -------------------------
+struct NeoxLayer {
+    QWeight wqkv, wdense, wfc, wproj;   // query_key_value [3e x e] (rows per head: q | k | v), attention.dense, mlp.dense_h_to_4h, mlp.dense_4h_to_h
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bdense, *bfc, *bproj;
+    __half *K, *V;                      // [n_ctx][e] by position / [e][n_ctx] transposed, as the reference lays out memory_k / memory_v (:233-247)
+};
+struct NeoxParams {
+    int n_layer, e, hd, n_head, n_ctx, n_vocab, n_rot, parallel_residual;
+    QWeight wte, lm_head;
+    const float *lnf_g, *lnf_b;
+    float kq_scale;
+    const float2 *rope_cs; int rope_half;
+    const uint16_t *lut_gelu, *lut_exp;
+    const int32_t *token; int *n_past;
+    float *x, *qkv, *q, *attn_out, *logits;     // residual stream [e], raw qkv [3e], roped q [e], attention branch output [e]
+    int4 *xpack_a, *xpack_d, *xpack_f;          // records: layer-norm output (K = e), attention rows (K = e), gelu output (K = 4e)
+};
+void neox_decode_enqueue(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int wtype, int n_kv_bucket, cudaStream_t st, int *launches);
+
 int decode_scratch_bytes(int e, int f, int hd, int n_ctx);
 bool decode_supported(const DecodeParams &P, int wtype);
 // cooperative launch on `st`; returns false if the kernel cannot be made resident (caller falls back to the per-op schedule)

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
 }
 
 // ---- mat-vec with fused epilogues --------------------------------------------------------------------------------------------------
-enum { EPI_RES = 0, EPI_QKV = 1, EPI_SILU = 2, EPI_LOGITS = 3 };
+enum { EPI_RES = 0, EPI_QKV = 1, EPI_SILU = 2, EPI_LOGITS = 3, EPI_BIAS = 4, EPI_GELU = 5 };   // BIAS / GELU: GPT-NeoX (bias adds, gelu table)
 
 struct MmvArgs {
     const int4 *xpack;            // input records
@@ -127,6 +127,8 @@ struct MmvArgs {
     int nst;                      // ring depth chosen by launch_mmv
     int pdl_early;                // trigger the dependents from the producer warp once every byte is requested (B200_PDL_EARLY, default 1)
     unsigned long long *prof;
+    // EPI_BIAS: dst = ((W x + bias) [+ add1]) [+ add2] in that order (ggml_add nodes of gptneox lib.rs:200,302,308-325); EPI_GELU: gelu(W x + bias) quantized
+    const float *bias, *add1, *add2; const uint16_t *lut_gelu;
     // tensor-parallel decode (tp.cuh): this rank owns rows [row0, row0 + w.N) of the full matrix; results go to buffer dst_buf of every rank
     TpCtx tp; TpSync ts; int64_t row0; int dst_buf;
 };
@@ -181,6 +183,27 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
                 A.V[(int64_t)(row - A.e - A.gqa) * A.n_ctx + p] = __float2half_rn(v);
             }
         });
+    } else if (EPI == EPI_BIAS) {
+        consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
+            if ((tid & 3) != 0 || row >= w.N) return;
+            float out = A.bias ? __fadd_rn(v, __ldg(A.bias + row)) : v;
+            if (A.add1) out = __fadd_rn(out, __ldcg(A.add1 + row));
+            if (A.add2) out = __fadd_rn(out, __ldcg(A.add2 + row));
+            A.dst[row] = out;
+        }, 1, A.prof);
+        if (A.n_past_inc && blockIdx.x == 0 && tid == 0) *A.n_past_inc = *A.n_past_inc + 1;
+    } else if (EPI == EPI_GELU) {   // one 32-row tile = one quant block of the next mat-vec's input (rows past N: zero activations)
+        consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
+            if ((tid & 3) == 0) stash[row & 31] = row < w.N ? __fadd_rn(v, __ldg(A.bias + row)) : 0.f;
+            compute_sync();
+            if (warp == 0) {
+                const float4 a = ((const float4 *)stash)[lane & 7];
+                float4 hm;
+                hm.x = lutf(A.lut_gelu, a.x); hm.y = lutf(A.lut_gelu, a.y); hm.z = lutf(A.lut_gelu, a.z); hm.w = lutf(A.lut_gelu, a.w);
+                pack_quad(hm, A.xpack_out + (row >> 5) * 4, lane, lane < 8, A.q81, A.off, A.scale16);
+            }
+            compute_sync();
+        }, 1, A.prof);
     } else {   // EPI_SILU
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
             if ((tid & 3) == 0) stash[row & 63] = v;
@@ -605,7 +628,142 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     if (launches) *launches = n;
 }
 
+// ---- GPT-NeoX --------------------------------------------------------------------------------------------------------------------------------
+// LayerNorm (ggml_compute_forward_norm_f32, LC/ggml.c:10063-10111) * gain + bias -> Q8 records.  Same shape as norm_pack_kernel: every CTA reduces
+// the whole row from registers (two passes: mean, then the variance of the centred values) and packs its own 32 blocks.
+__global__ void __launch_bounds__(256) ln_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, const float *__restrict__ bias, int4 *__restrict__ pack,
+                                                      int e, int q81, int off, int scale16) {
+    __shared__ double shd[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
+    constexpr int MAXV = 8;                                     // n_embd <= 8192
+    const int nv = e / 4, mine = blockIdx.x * 256 + tid;
+    float4 v[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) { const int i = tid + k * 256; v[k] = i < nv ? __ldcg((const float4 *)x + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    const bool active = mine < nv;
+    const float4 gv = active ? __ldg((const float4 *)gain + mine) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bv = active ? __ldg((const float4 *)bias + mine) : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto total = [&](double s) {
+        s = warp_sum(s);
+        __syncthreads();
+        if (lane == 0) shd[warp] = s;
+        __syncthreads();
+        return ((shd[0] + shd[1]) + (shd[2] + shd[3])) + ((shd[4] + shd[5]) + (shd[6] + shd[7]));
+    };
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) if (tid + k * 256 < nv) { s += (double)v[k].x; s += (double)v[k].y; s += (double)v[k].z; s += (double)v[k].w; }
+    const float mean = (float)(total(s) / (double)e);
+    double s2 = 0.0;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < MAXV; k++) if (tid + k * 256 < nv) {
+        float4 c;
+        c.x = __fsub_rn(v[k].x, mean); c.y = __fsub_rn(v[k].y, mean); c.z = __fsub_rn(v[k].z, mean); c.w = __fsub_rn(v[k].w, mean);
+        s2 += (double)__fmul_rn(c.x, c.x); s2 += (double)__fmul_rn(c.y, c.y); s2 += (double)__fmul_rn(c.z, c.z); s2 += (double)__fmul_rn(c.w, c.w);
+        if (k == (int)blockIdx.x) xv = c;                       // float4 index tid + k * 256 == mine
+    }
+    const float variance = (float)(total(s2) / (double)e);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
+    float4 y;
+    y.x = __fadd_rn(__fmul_rn(__fmul_rn(xv.x, scale), gv.x), bv.x); y.y = __fadd_rn(__fmul_rn(__fmul_rn(xv.y, scale), gv.y), bv.y);
+    y.z = __fadd_rn(__fmul_rn(__fmul_rn(xv.z, scale), gv.z), bv.z); y.w = __fadd_rn(__fmul_rn(__fmul_rn(xv.w, scale), gv.w), bv.w);
+    pack_quad(y, pack + (active ? mine >> 3 : 0) * 4, lane, active, q81, off, scale16);
+}
+
+// qkv [3e] (rows per head: q | k | v, bias added) -> RoPE mode 2 on q and k (ggml neox branch, LC/ggml.c:11876-11897: EVERY block of n_rot dims of the head
+// is rotated, pairs (c, c + n_rot/2)), q -> [e], k -> f16 cache row n_past, v -> f16 cache column n_past (gptneox lib.rs:205-247).  One thread per channel.
+__global__ void __launch_bounds__(256) neox_rope_store_kernel(const float *__restrict__ qkv, float *__restrict__ q, __half *__restrict__ Kl, __half *__restrict__ Vl,
+                                                              const int *__restrict__ n_past, const float2 *__restrict__ rope_cs, int rope_half, int n_rot, int hd, int e, int n_ctx) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= e) return;
+    const int p = __ldcg(n_past);
+    const int h = i / hd, c = i - h * hd;
+    const float *base = qkv + (int64_t)h * 3 * hd;
+    const int hb = n_rot / 2, ib = c / n_rot, r = c - ib * n_rot;
+    float qo = __ldcg(base + c), ko = __ldcg(base + hd + c);
+    if (ib < hd / n_rot) {
+        const bool lo = r < hb;
+        const int partner = lo ? c + hb : c - hb;
+        const float2 cs = __ldg(rope_cs + (int64_t)p * rope_half + ib * hb + (lo ? r : r - hb));
+        const float qp = __ldcg(base + partner), kp = __ldcg(base + hd + partner);
+        // x0 = element of the lower half, x1 = upper: out0 = fma(x0, cos, -(x1 sin)), out1 = fma(x0, sin, x1 cos)  (rowops.cu::rope_kernel)
+        qo = lo ? __fmaf_rn(qo, cs.x, -__fmul_rn(qp, cs.y)) : __fmaf_rn(qp, cs.y, __fmul_rn(qo, cs.x));
+        ko = lo ? __fmaf_rn(ko, cs.x, -__fmul_rn(kp, cs.y)) : __fmaf_rn(kp, cs.y, __fmul_rn(ko, cs.x));
+    }
+    q[i] = qo;
+    Kl[(int64_t)p * e + i] = __float2half_rn(ko);
+    Vl[(int64_t)i * n_ctx + p] = __float2half_rn(__ldcg(base + 2 * hd + c));
+}
+
+template <int TYPE>
+void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n_kv_bucket, cudaStream_t st, int *launches) {
+    const int q81 = has_min(TYPE) ? 1 : 0, off = TYPE == T_Q5_0 ? 16 : 0, s16 = TYPE == T_Q4_0 ? 1 : 0;
+    const int e = P.e;
+    int n = 0;
+    get_rows_q(P.wte, P.token, P.x, 1, st); n++;
+    const int nlay = (n_kv_bucket + 63) / 64 * 64;
+    const size_t fa_smem = (((size_t)nlay * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (nlay + 32) * 2;
+    B200_ASSERT(P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024 && e <= 8192);
+    static size_t fa_set = 48 * 1024;
+    if (fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
+    const dim3 ln_grid((e / 4 + 255) / 256);
+    const TpCtx T{}; const TpSync S{};
+    for (int il = 0; il < P.n_layer; il++) {
+        const NeoxLayer &L = layers[il];
+        launch_k(ln_pack_kernel, ln_grid, dim3(256), 0, st, (const float *)P.x, L.ln1_g, L.ln1_b, P.xpack_a, e, q81, off, s16); n++;          // :192-196
+        MmvArgs A{}; A.xpack = P.xpack_a; A.dst = P.qkv; A.bias = L.bqkv;
+        launch_mmv<TYPE, EPI_BIAS>(L.wqkv, A, st); n++;                                                                                      // :199-200
+        launch_k(neox_rope_store_kernel, dim3((e + 255) / 256), dim3(256), 0, st, (const float *)P.qkv, P.q, L.K, L.V, (const int *)P.n_past, P.rope_cs, P.rope_half,
+                 P.n_rot, P.hd, e, P.n_ctx); n++;                                                                                             // :205-247
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(P.n_head * (P.hd / 32)); cfg.blockDim = dim3(ATH); cfg.dynamicSmemBytes = fa_smem; cfg.stream = st;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = P.hd / 32; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
+            B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
+                                          (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head, e, P.n_ctx, nlay, q81, off, s16,
+                                          (unsigned long long *)nullptr, T, S, 0));                                                           // :250-298
+            n++;
+        }
+        // attention.dense (+bias); sequential residual: ff_in = that + inpL                                                                    :301-312
+        MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.attn_out; Bo.bias = L.bdense; Bo.add1 = P.parallel_residual ? nullptr : P.x;
+        launch_mmv<TYPE, EPI_BIAS>(L.wdense, Bo, st); n++;
+        // mlp: LayerNorm of inpL (parallel residual) or of ff_in                                                                                :313-316 / ffn
+        launch_k(ln_pack_kernel, ln_grid, dim3(256), 0, st, (const float *)(P.parallel_residual ? P.x : P.attn_out), L.ln2_g, L.ln2_b, P.xpack_a, e, q81, off, s16); n++;
+        MmvArgs C{}; C.xpack = P.xpack_a; C.xpack_out = P.xpack_f; C.bias = L.bfc; C.lut_gelu = P.lut_gelu; C.q81 = q81; C.off = off; C.scale16 = s16;
+        launch_mmv<TYPE, EPI_GELU>(L.wfc, C, st); n++;
+        // parallel: inpL = ((proj + bias) + attn) + inpL; sequential: inpL = (proj + bias) + ff_in                                              :317-325
+        MmvArgs D{}; D.xpack = P.xpack_f; D.dst = P.x; D.bias = L.bproj; D.add1 = P.attn_out; D.add2 = P.parallel_residual ? P.x : nullptr;
+        launch_mmv<TYPE, EPI_BIAS>(L.wproj, D, st); n++;
+    }
+    launch_k(ln_pack_kernel, ln_grid, dim3(256), 0, st, (const float *)P.x, P.lnf_g, P.lnf_b, P.xpack_a, e, q81, off, s16); n++;                     // :332-334
+    MmvArgs Z{}; Z.xpack = P.xpack_a; Z.dst = P.logits; Z.n_past_inc = P.n_past;
+    launch_mmv<TYPE, EPI_BIAS>(P.lm_head, Z, st); n++;                                                                                        // :342
+    B200_CHECK(cudaGetLastError());
+    if (launches) *launches = n;
+}
+
 }  // namespace
+
+void neox_decode_enqueue(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int wtype, int n_kv_bucket, cudaStream_t st, int *launches) {
+    switch (wtype) {
+        case T_Q4_0: neox_ops_t<T_Q4_0>(P, layers, n_kv_bucket, st, launches); break;
+        case T_Q4_1: neox_ops_t<T_Q4_1>(P, layers, n_kv_bucket, st, launches); break;
+        case T_Q5_0: neox_ops_t<T_Q5_0>(P, layers, n_kv_bucket, st, launches); break;
+        case T_Q5_1: neox_ops_t<T_Q5_1>(P, layers, n_kv_bucket, st, launches); break;
+        case T_Q8_0: neox_ops_t<T_Q8_0>(P, layers, n_kv_bucket, st, launches); break;
+        default: B200_ASSERT(!"neox_decode_enqueue: unsupported weight type");
+    }
+}
 
 // Enqueue one decode step (position read from *P.n_past on the device) on `st`.  n_kv_bucket >= n_past + 1 sizes the KQ grid.
 void decode_ops_enqueue(const DecodeParams &P, const std::vector<DecodeLayer> &layers, int wtype, int n_kv_bucket, int4 *xpack_a, cudaStream_t st, int *launches) {

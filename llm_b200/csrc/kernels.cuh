@@ -56,6 +56,11 @@ bool mmv_exact_stream_supported(const QWeight &w);
 void quantize_act_pack(int wtype, const float *x, int4 *pack, int64_t K, cudaStream_t st);
 void mul_mat_vec_q_exact_stream(const QWeight &w, const int4 *xpack, float *dst, const float *addend, cudaStream_t st);
 
+// ---- synth.cu : seeded synthetic tensors generated in HBM (bench / tests) ------------------------------------------------------------
+void synth_qweight(const QWeight &w, uint64_t seed, cudaStream_t st);
+void synth_gain(float *g, int64_t n, uint64_t seed, cudaStream_t st);                       // 1 + 0.1 N(0,1)
+void scale_shift_f32(float *p, int64_t n, float a, float b, cudaStream_t st);                // p = p * a + b
+
 // ---- rowops.cu : warp/block-reduce kernels ------------------------------------------------------------------------
 struct Luts { const uint16_t *silu, *gelu, *exp; };   // 3 x 64 Ki fp16 tables built on the host with libm (LC/ggml.c:4313-4326)
 const Luts &luts();                                   // uploaded on first use

@@ -78,6 +78,14 @@ void synth_qweight(const QWeight &w, uint64_t seed, cudaStream_t st) {
     synth_q_kernel<<<(unsigned)((nblk + 7) / 8), 256, 0, st>>>(w, seed, 1.0f / sqrtf((float)w.K));
     B200_CHECK(cudaGetLastError());
 }
+__global__ void scale_shift_kernel(float *p, int64_t n, float a, float b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = p[i] * a + b;
+}
+void scale_shift_f32(float *p, int64_t n, float a, float b, cudaStream_t st) {
+    scale_shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, a, b);
+    B200_CHECK(cudaGetLastError());
+}
 void synth_gain(float *g, int64_t n, uint64_t seed, cudaStream_t st) {
     synth_gain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, n, seed);
     B200_CHECK(cudaGetLastError());
