@@ -21,12 +21,18 @@ def ref_model(hp, tens, n_batch=256):
     return B.RefLib("ref").neox(hp, tens, n_threads=8, n_batch=n_batch)
 
 
+CFGS = {   # K = 256 (8 quant blocks: the streaming mat-vec's granularity), head sizes 64 / 32, rotary dims < and == head size, both residual forms
+    "par": dict(n_vocab=384, n_ctx=128, n_embd=256, n_head=4, n_layer=2, n_rot=16, use_parallel_residual=1),
+    "seq": dict(n_vocab=384, n_ctx=128, n_embd=256, n_head=8, n_layer=2, n_rot=32, use_parallel_residual=0),
+}
+
+
 @pytest.mark.parametrize("name", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
-@pytest.mark.parametrize("cfg", ["neox-tiny", "neox-tiny-seq"])
+@pytest.mark.parametrize("cfg", ["par", "seq"])
 def test_neox_native_vs_reference(orc, cfg, name):
     from llm_b200.neox import GptNeoX
     t = B.QUANT_TYPES[name]
-    hp, tens = synth.make_neox(synth.NEOX_CONFIGS[cfg], t, orc.quantize)
+    hp, tens = synth.make_neox(CFGS[cfg], t, orc.quantize)
     toks = synth.make_tokens(hp, 60)
     mr = ref_model(hp, tens, 64)
     m = GptNeoX(hp, tens)
