@@ -38,12 +38,23 @@ uint64_t data_size(int32_t type, uint64_t n) {
     switch (type) {
         case b200::T_F32: return n * 4;
         case b200::T_F16: return n * 2;
-        case b200::T_Q4_0: case b200::T_Q4_1: case b200::T_Q5_0: case b200::T_Q5_1: case b200::T_Q8_0:
+        case b200::T_Q4_0: case b200::T_Q4_1: case b200::T_Q5_0: case b200::T_Q5_1: case b200::T_Q8_0: case b200::T_Q8_1:
             return n / b200::QK * (uint64_t)b200::ggml_block_bytes(type);
+        // K-quants (LC/k_quants.h, QK_K = 256): parsed and sized like the reference's loader does; this backend has no kernels for them yet, so
+        // b200_llama_load_file reports the tensor by name instead of failing the whole parse (GGJT v3 "Q4_0" files of the vendored llama.cpp
+        // quantizer carry output.weight as Q6_K, LC/llama.cpp:2938-2944)
+        case 10: return n / 256 * 84;  case 11: return n / 256 * 110; case 12: return n / 256 * 144; case 13: return n / 256 * 176; case 14: return n / 256 * 210;
+        case b200::T_I8: return n; case b200::T_I32: return n * 4;
         default: return 0;
     }
 }
-bool known_type(int32_t t) { return t == b200::T_F32 || t == b200::T_F16 || b200::is_quant(t); }
+// every ElementType the reference's Type::try_from accepts (crates/ggml/src/lib.rs:156-230)
+bool known_type(int32_t t) { return t == b200::T_F32 || t == b200::T_F16 || b200::is_quant(t) || t == b200::T_Q8_1 || (t >= 10 && t <= 14) || t == b200::T_I8 || t == b200::T_I32; }
+const char *type_name(int32_t t) {
+    switch (t) { case 0: return "F32"; case 1: return "F16"; case 2: return "Q4_0"; case 3: return "Q4_1"; case 6: return "Q5_0"; case 7: return "Q5_1"; case 8: return "Q8_0";
+                 case 9: return "Q8_1"; case 10: return "Q2_K"; case 11: return "Q3_K"; case 12: return "Q4_K"; case 13: return "Q5_K"; case 14: return "Q6_K"; case 16: return "I8"; case 18: return "I32"; }
+    return "?";
+}
 
 }  // namespace
 
@@ -68,7 +79,7 @@ void b200_ggml_close(b200_ggml_file *f) {
     delete f;
 }
 
-b200_ggml_file *b200_ggml_open_arch(const char *path, int32_t arch, int *err) {
+static b200_ggml_file *open_arch_impl(const char *path, int32_t arch, int *err) {
     int dummy; if (!err) err = &dummy;
     if (arch < 0 || arch > 2) { *err = B200_ERR_BAD_ARG; return nullptr; }
     *err = B200_OK;
@@ -103,6 +114,7 @@ b200_ggml_file *b200_ggml_open_arch(const char *path, int32_t arch, int *err) {
     if (arch == B200_ARCH_GPTNEOX && f->hp[6] > 1) return fail(B200_ERR_IO);                        // read_bool: InvalidData
 
     const bool scored = f->magic == MAGIC_GGMF || f->magic == MAGIC_GGJT;
+    if ((uint64_t)f->hp[0] > (f->size - pos) / 4) return fail(B200_ERR_IO);       // every token record takes at least 4 bytes: a corrupt count cannot ask for gigabytes
     f->tokens.reserve((size_t)f->hp[0]);
     for (int32_t i = 0; i < f->hp[0]; i++) {
         const uint32_t len = rd32();
@@ -139,6 +151,12 @@ b200_ggml_file *b200_ggml_open_arch(const char *path, int32_t arch, int *err) {
         f->tensors.push_back(t);
     }
     return f;
+}
+
+// no C++ exception (e.g. std::bad_alloc on a hostile header) may cross the C ABI: it becomes LoadError::Io
+b200_ggml_file *b200_ggml_open_arch(const char *path, int32_t arch, int *err) {
+    try { return open_arch_impl(path, arch, err); }
+    catch (...) { if (err) *err = B200_ERR_IO; return nullptr; }
 }
 
 b200_ggml_file *b200_ggml_open(const char *path, int *err) { return b200_ggml_open_arch(path, B200_ARCH_LLAMA, err); }
@@ -196,13 +214,14 @@ int b200_ggml_llama_hparams(const b200_ggml_file *f, b200_llama_hparams *out, in
     if (llama_ftype) *llama_ftype = (int32_t)((uint32_t)f->hp[6] % 1000u);
     if (quantization_version) *quantization_version = qv;
     bool any_quant = false;
+    out->wtype = -1;                                                             // "not found" (F32 = 0 is a valid element type)
     for (const TensorInfo &t : f->tensors) {
         any_quant |= b200::is_quant(t.type);
         if (t.name == "layers.0.feed_forward.w1.weight") out->n_ff = (int32_t)t.ne[1];
         if (t.name == "layers.0.attention.wq.weight") out->wtype = t.type;
     }
     if (any_quant && qv != 2) return B200_ERR_QUANTIZATION_VERSION;
-    if (out->n_ff == 0 || out->wtype == 0) return B200_ERR_UNKNOWN_TENSOR;
+    if (out->n_ff == 0 || out->wtype < 0) return B200_ERR_UNKNOWN_TENSOR;
     return B200_OK;
 }
 
@@ -247,27 +266,42 @@ int b200_ggml_write_llama(const char *path, const b200_llama_hparams *hp, int32_
 }
 
 // llm::load::<Llama>(path, params): parse, build the model for the file's geometry, upload every tensor from the mapping.
-b200_model *b200_llama_load_file(const char *path, int32_t context_size, float rope_freq_base, float rope_freq_scale, int *err) {
+// n_gqa > 1: ModelParameters::n_gqa (grouped-query attention, e.g. 8 for LLaMA-2 70B): n_head_kv = n_head / n_gqa (llama lib.rs:403-447).
+b200_model *b200_llama_load_file_gqa(const char *path, int32_t context_size, float rope_freq_base, float rope_freq_scale, int32_t n_gqa, int *err) {
     int dummy; if (!err) err = &dummy;
     b200_ggml_file *f = b200_ggml_open(path, err);
     if (!f) return nullptr;
     b200_llama_hparams hp;
     *err = b200_ggml_llama_hparams(f, &hp, nullptr, nullptr, nullptr);
     if (*err != B200_OK) { b200_ggml_close(f); return nullptr; }
+    if (!b200::is_quant(hp.wtype)) {            // F16 / F32 / K-quant files parse, but this backend streams the five 32-element block formats only
+        fprintf(stderr, "llm_b200: %s: layers.0.attention.wq.weight is %s; this backend loads Q4_0/Q4_1/Q5_0/Q5_1/Q8_0 weights\n", path, type_name(hp.wtype));
+        *err = B200_ERR_UNSUPPORTED_ELEMENT_TYPE; b200_ggml_close(f); return nullptr;
+    }
     if (context_size > 0) hp.context_size = context_size;
     if (rope_freq_base > 0.f) hp.rope_freq_base = rope_freq_base;
     if (rope_freq_scale > 0.f) hp.rope_freq_scale = rope_freq_scale;
+    if (n_gqa > 1) { if (hp.n_head % n_gqa) { *err = B200_ERR_BAD_ARG; b200_ggml_close(f); return nullptr; } hp.n_head_kv = hp.n_head / n_gqa; }
     b200_model *m = b200_llama_new(&hp);
     if (!m) { *err = B200_ERR_BAD_ARG; b200_ggml_close(f); return nullptr; }
     for (size_t i = 0; i < f->tensors.size(); i++) {
         const TensorInfo &t = f->tensors[i];
-        const int rc = b200_model_load_tensor(m, t.name.c_str(), t.type, f->map + t.offset, (size_t)t.nbytes);
+        const bool is_norm = t.n_dims == 1;
+        if (!is_norm && t.type != hp.wtype) {     // one weight type per model (QWeight planes are per matrix, the decode graph is instantiated per type)
+            fprintf(stderr, "llm_b200: %s: tensor %s is %s, the model's weight type is %s: mixed-type files are not supported by this backend\n", path, t.name.c_str(),
+                    type_name(t.type), type_name(hp.wtype));
+            *err = B200_ERR_UNSUPPORTED_ELEMENT_TYPE; b200_model_free(m); b200_ggml_close(f); return nullptr;
+        }
+        const int rc = b200_model_load_tensor_shaped(m, t.name.c_str(), t.type, t.n_dims, t.ne[0], t.ne[1], f->map + t.offset, (size_t)t.nbytes);
         if (rc != B200_OK) { *err = rc; b200_model_free(m); b200_ggml_close(f); return nullptr; }
     }
     if (!b200_model_is_loaded(m)) { *err = B200_ERR_NOT_LOADED; b200_model_free(m); b200_ggml_close(f); return nullptr; }
     b200_ggml_close(f);
     *err = B200_OK;
     return m;
+}
+b200_model *b200_llama_load_file(const char *path, int32_t context_size, float rope_freq_base, float rope_freq_scale, int *err) {
+    return b200_llama_load_file_gqa(path, context_size, rope_freq_base, rope_freq_scale, 1, err);
 }
 
 }  // extern "C"

@@ -469,6 +469,16 @@ int b200_model_load_tensor(b200_model *m, const char *name, int32_t type, const 
     return B200_OK;
 }
 
+// TensorLoader::load checks the dims too (TensorWrongSize): a file whose tensor has the right byte count but swapped / wrong dims must not load
+int b200_model_load_tensor_shaped(b200_model *m, const char *name, int32_t type, int32_t n_dims, int64_t ne0, int64_t ne1, const void *host_data, size_t nbytes) {
+    if (!m || !name) return B200_ERR_BAD_ARG;
+    b200_model::Slot s; int id;
+    if (!m->lookup(name, s, id)) return B200_ERR_UNKNOWN_TENSOR;
+    if (s.is_q) { if (n_dims != 2 || ne0 != s.q.K || ne1 != (s.chunk ? s.rows : s.q.N)) return B200_ERR_TENSOR_SHAPE; }
+    else if (n_dims != 1 || ne0 != s.n) return B200_ERR_TENSOR_SHAPE;
+    return b200_model_load_tensor(m, name, type, host_data, nbytes);
+}
+
 int b200_model_read_tensor(b200_model *m, const char *name, void *host_out, size_t nbytes) {
     if (!m || !name || !host_out) return B200_ERR_BAD_ARG;
     b200_model::Slot s; int id;

@@ -89,7 +89,7 @@ def test_load_errors(tmp_path, case, kind):
     elif case == "q4_row_not_64":
         _raw_file(path, tensors=[(2, b"w", 2, (32, 2), b"\0" * 36)])                 # loader.rs:249-254
     elif case == "unknown_type":
-        _raw_file(path, tensors=[(1, b"k", 12, (256,), b"\0" * 144)])                # a K-quant id: not an element type of this backend
+        _raw_file(path, tensors=[(1, b"k", 5, (256,), b"\0" * 144)])                 # 5 = the removed Q4_2: not an ElementType of the reference either
     elif case == "truncated_tensor":
         _raw_file(path, tensors=[(1, b"x", 0, (64,), f32(10))])
     elif case == "truncated_header":
@@ -203,3 +203,14 @@ def test_load_file_rejects_incomplete_and_mismatched_models(orc, tmp_path):
     with pytest.raises(loader.LoadError) as e:
         loader.load(p, llm_b200.ModelParameters(context_size=hp["n_ctx"]))
     assert e.value.kind == "UnknownTensor"
+
+
+def test_k_quant_tensors_parse_like_the_reference(tmp_path):
+    """the reference's Type::try_from accepts the K-quant element types (crates/ggml/src/lib.rs:156-230): a file carrying them parses, with the block
+    sizes of LC/k_quants.h (QK_K = 256); only LOADING such a tensor into this backend is refused"""
+    from llm_b200 import loader
+    path = str(tmp_path / "kq.bin")
+    _raw_file(path, tensors=[(1, b"q4k", 12, (256,), b"\0" * 144), (1, b"q6k", 14, (512,), b"\0" * 420), (1, b"q2k", 10, (256,), b"\0" * 84)])
+    f = loader.GgmlFile(path)
+    infos = {t.name: t for t in f.tensors}
+    assert infos["q4k"].nbytes == 144 and infos["q6k"].nbytes == 420 and infos["q2k"].nbytes == 84
