@@ -15,6 +15,11 @@
  * Where the per-node seam (ggml_b200.h) replays the reference's graph one node per call, this front end owns the whole
  * forward pass: a static schedule of fused sm_100a kernels (captured as a CUDA graph for decode), weights and KV cache
  * resident in HBM.  Both front ends run the same kernels and are held to the same parity bar.
+ *
+ * Threading / device contract: one process drives ONE device (b200_init picks it; multi-GPU = one process per GPU, see b200_llama_new_tp), and
+ * the entry points of this header are to be called from one host thread at a time -- the launch code keeps per-process caches (kernel attributes,
+ * occupancy tables, the RoPE / LUT tables) that are not synchronised.  Everything is ordered on the backend's single non-blocking stream.
+ * b200_session_evaluate validates token ids; b200_session_evaluate_device takes them from HBM unchecked: ids in [0, n_vocab) are its precondition.
  */
 #ifndef LLM_B200_H
 #define LLM_B200_H
