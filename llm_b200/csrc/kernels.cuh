@@ -50,6 +50,11 @@ bool prefill_gemm_tc5();         // session.cu: B200_PREFILL_GEMM != "mma" (the 
 int exact_tc5_check_timeout();   // debugging aid of the op-level entry points: non-zero if a pipeline barrier of the kernel ever timed out
 void mul_mat_q_exact_tc5(const QWeight &w, const __half *xh, const float2 *xds, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
 
+// ---- mmq_tc5.cu : order-free (NON-conformant) fused dequant -> tcgen05 GEMM, f16 operands, f32 accumulation over K in TMEM --------------------
+void cvt_act_f16(const float *x, int64_t ldx, __half *xh, int64_t K, int64_t B, cudaStream_t st);      // f32 rows -> fp16 row-major [B][K]
+void mul_mat_q_fast_tc5(const QWeight &w, const __half *xh, float *dst, int64_t ldd, int64_t B, const float *addend, int64_t lda, cudaStream_t st);
+int fast_tc5_check_timeout();
+
 // ---- exact_stream.cu : the bit-exact decode mat-vec at HBM speed (TMA bulk-copy ring + AVX2 lane chains) ----------------------------
 bool mmv_exact_stream_supported(const QWeight &w);
 // bit-faithful activation quantizer emitting 16-byte records per (block, word): see exact_stream.cu

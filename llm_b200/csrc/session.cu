@@ -165,6 +165,7 @@ void matmul(b200_session *s, const QWeight &w, const float *x, float *dst, int64
     if (!fast)       mul_mat_q_exact(w, s->xq, s->xds, dst, ldd, B, addend, lda, st);
     else if (B == 1) mul_mat_vec_q(w, s->xq, s->xds, dst, addend, st);
     else if (B < 16) mul_mat_q_simple(w, s->xq, s->xds, dst, ldd, B, addend, lda, st);
+    else if (prefill_gemm_tc5() && B >= 64) { cvt_act_f16(x, w.K, s->xh, w.K, B, st); mul_mat_q_fast_tc5(w, s->xh, dst, ldd, B, addend, lda, st); }   // fused dequant -> tcgen05 GEMM
     else             mul_mat_q(w, s->xq, s->xds, dst, ldd, B, addend, lda, st);
     L.n += 2;
 }
@@ -907,6 +908,12 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
         mul_mat_q_exact_tc5(w, xh, xds, dd, N, B, nullptr, 0, st);
         B200_CHECK(cudaStreamSynchronize(st));
         if (exact_tc5_check_timeout() != 0) return B200_ERR_IO;
+    } else if (impl == B200_MM_FAST_TC5) {
+        __half *xh = (__half *)R.op_arena.get((size_t)B * K * 2 + 16, st);
+        cvt_act_f16(dx, K, xh, K, B, st);
+        mul_mat_q_fast_tc5(w, xh, dd, N, B, nullptr, 0, st);
+        B200_CHECK(cudaStreamSynchronize(st));
+        if (fast_tc5_check_timeout() != 0) return B200_ERR_IO;
     } else if (impl == B200_MM_EXACT_STREAM) {
         if (!mmv_exact_stream_supported(w)) return B200_ERR_BAD_ARG;
         int4 *pack = (int4 *)R.op_arena.get((size_t)(K / QK) * 64, st);
@@ -937,11 +944,13 @@ int b200_op_bench_mul_mat(int32_t wtype, int64_t K, int64_t N, int64_t B, int32_
     __half *xh = (__half *)R.op_arena.get(xh_bytes(K, B) + 16, st);
     int8_t *xq = (int8_t *)R.op_arena.get((size_t)B * K, st);
     synth_gain(dx, B * K, 12345u, st);
-    if (impl == B200_MM_EXACT_TC5) quantize_act_f16_rm(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
+    if (impl == B200_MM_FAST_TC5) cvt_act_f16(dx, K, xh, K, B, st);
+    else if (impl == B200_MM_EXACT_TC5) quantize_act_f16_rm(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
     else if (impl == B200_MM_EXACT_MMA) quantize_act_f16(vec_dot_type(wtype), dx, K, xh, xds, K, B, st);
     else quantize_act(vec_dot_type(wtype), dx, K, xq, xds, K, B, st);
     auto run = [&]() {
-        if (impl == B200_MM_EXACT_TC5) mul_mat_q_exact_tc5(w, xh, xds, dd, N, B, nullptr, 0, st);
+        if (impl == B200_MM_FAST_TC5) mul_mat_q_fast_tc5(w, xh, dd, N, B, nullptr, 0, st);
+        else if (impl == B200_MM_EXACT_TC5) mul_mat_q_exact_tc5(w, xh, xds, dd, N, B, nullptr, 0, st);
         else if (impl == B200_MM_EXACT_MMA) mul_mat_q_exact_mma(w, xh, xds, dd, N, B, nullptr, 0, st);
         else mul_mat_q(w, xq, xds, dd, N, B, nullptr, 0, st);
     };
@@ -957,6 +966,7 @@ int b200_op_bench_mul_mat(int32_t wtype, int64_t K, int64_t N, int64_t B, int32_
     *ms_out = ms / iters;
     B200_CHECK(cudaEventDestroy(e0)); B200_CHECK(cudaEventDestroy(e1));
     if (impl == B200_MM_EXACT_TC5 && exact_tc5_check_timeout() != 0) return B200_ERR_IO;
+    if (impl == B200_MM_FAST_TC5 && fast_tc5_check_timeout() != 0) return B200_ERR_IO;
     return B200_OK;
 }
 

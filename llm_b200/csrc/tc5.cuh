@@ -25,7 +25,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Spin with a watchdog: a protocol bug must not hang the GPU box (a hang is a strike).  After ~1 s without progress the thread records
 // (bar, parity, block, thread) in g_timeout, turns "dead" (all its later waits return at once) and the kernel runs to completion with
 // garbage results; the host reads g_timeout (tc5_check_timeout) in the op-level entry points and the tests.
-__device__ unsigned int g_timeout[8];
+static __device__ unsigned int g_timeout[8];   // one copy per translation unit (each kernel file has its own *_check_timeout)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool &dead) {
     if (dead || mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();

@@ -137,6 +137,22 @@ def test_mul_mat_fast_kernels_vs_oracle(L, orc, name, t, K, N, Bn, impl):
 
 
 @pytest.mark.parametrize("name,t", TYPES)
+@pytest.mark.parametrize("K,N,Bn", [(4096, 256, 128), (704, 100, 40), (11008, 300, 200), (2048, 513, 512), (64, 16, 129)])
+def test_mul_mat_fast_tcgen05_vs_oracle(L, orc, name, t, K, N, Bn):
+    """fused dequant -> tcgen05 GEMM (mmq_tc5.cu), the order-free fast mode: fp16 operands, f32 accumulation in TMEM.  Held to 2e-3 of the row scale
+    (it is NOT the conformant path: activations are not Q8-quantized and the summation order is the tensor core's)"""
+    rng = np.random.default_rng(K * 17 + N + t)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    x = (rng.standard_normal((Bn, K)) * 2.5).astype(np.float32)
+    wq = orc.quantize(t, w)
+    deq = np.stack([orc.to_float(t, wq[i], K) for i in range(N)])
+    want = x.astype(np.float64) @ deq.astype(np.float64).T                    # exact product with the dequantized weights, unquantized activations
+    got = np.empty((Bn, N), np.float32)
+    assert L.b200_op_mul_mat(t, wq.ctypes.data, K, N, x.ctypes.data, Bn, got.ctypes.data, 8) == 0
+    assert rel(got, want) <= 2e-3, (name, K, N, Bn, rel(got, want))
+
+
+@pytest.mark.parametrize("name,t", TYPES)
 def test_mul_mat_three_kernels_agree(L, orc, name, t):
     """decode mat-vec, CUDA-core GEMM and tensor-core GEMM are the same arithmetic up to f32 summation order"""
     rng = np.random.default_rng(11 + t)
