@@ -103,6 +103,7 @@ def lib():
     L.b200_llama_load_file.restype = vp
     L.b200_llama_load_file.argtypes = [C.c_char_p, i32, C.c_float, C.c_float, C.POINTER(C.c_int)]
     L.b200_op_quantize_act.argtypes = [i32, vp, i64, i64, vp, vp, vp]
+    L.b200_op_quantize_weights.argtypes = [i32, vp, i64, i64, vp]
     L.b200_op_mul_mat.argtypes = [i32, vp, i64, i64, vp, i64, vp, i32]
     _lib = L
     return L

@@ -64,6 +64,7 @@ void mul_mat_vec_q_exact_stream(const QWeight &w, const int4 *xpack, float *dst,
 // ---- synth.cu : seeded synthetic tensors generated in HBM (bench / tests) ------------------------------------------------------------
 void synth_qweight(const QWeight &w, uint64_t seed, cudaStream_t st);
 void synth_gain(float *g, int64_t n, uint64_t seed, cudaStream_t st);                       // 1 + 0.1 N(0,1)
+void quantize_weights(const QWeight &w, const float *src, cudaStream_t st);                  // ggml_quantize_q* on the GPU: f32 [N][K] -> planes, bit-exact
 void scale_shift_f32(float *p, int64_t n, float a, float b, cudaStream_t st);                // p = p * a + b
 
 // ---- rowops.cu : warp/block-reduce kernels ------------------------------------------------------------------------

@@ -927,6 +927,25 @@ int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, con
     return B200_OK;
 }
 
+// ggml_quantize_q{4_0,4_1,5_0,5_1,8_0} on the GPU (crates/llm-base/src/quantize.rs:320-414 calls them per tensor): f32 rows in, GGML blocks out
+int b200_op_quantize_weights(int32_t wtype, const float *w_host, int64_t K, int64_t N, void *ggml_blocks_out) {
+    if (!is_quant(wtype) || !w_host || !ggml_blocks_out || K % QK) return B200_ERR_BAD_ARG;
+    Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
+    cudaStream_t st = R.stream;
+    float *dw = (float *)R.op_arena.get((size_t)N * K * 4, st);
+    B200_CHECK(cudaMemcpyAsync(dw, w_host, (size_t)N * K * 4, cudaMemcpyHostToDevice, st));
+    QWeight w;
+    const size_t pb = qweight_layout(w, wtype, K, N, nullptr);
+    qweight_layout(w, wtype, K, N, R.op_arena.get(pb, st));
+    quantize_weights(w, dw, st);
+    const size_t raw_bytes = (size_t)N * (K / QK) * ggml_block_bytes(wtype);
+    void *raw = R.op_arena.get(raw_bytes, st);
+    unpack_weights(w, raw, st);
+    B200_CHECK(cudaMemcpyAsync(ggml_blocks_out, raw, raw_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
 // Kernel-only timing of one weight mat-mul on device-resident synthetic operands (seeded random weights and activations): used by
 // tools/prefill_gemm_bench.py and bench.py's prefill roofline; impl = B200_MM_EXACT_MMA / B200_MM_EXACT_TC5 / B200_MM_TENSOR
 int b200_op_bench_mul_mat(int32_t wtype, int64_t K, int64_t N, int64_t B, int32_t impl, int32_t iters, float *ms_out) {

@@ -137,6 +137,23 @@ def test_mul_mat_fast_kernels_vs_oracle(L, orc, name, t, K, N, Bn, impl):
 
 
 @pytest.mark.parametrize("name,t", TYPES)
+def test_weight_quantizer_bit_exact(L, orc, name, t):
+    """ggml_quantize_q* on the GPU (the call crates/llm-base/src/quantize.rs:365-377 makes per tensor): identical GGML blocks, incl. all-zero blocks,
+    blocks whose extreme value is positive / negative / repeated, and large dynamic range"""
+    rng = np.random.default_rng(99 + t)
+    K, N = 4096, 67
+    w = (rng.standard_normal((N, K)) * rng.uniform(1e-3, 30, (N, 1))).astype(np.float32)
+    w[3, :64] = 0.0
+    w[5, 32:64] = np.abs(w[5, 32:64]); w[5, 40] = w[5, 32:64].max()           # tie for the maximum
+    w[6, 0:32] = -np.abs(w[6, 0:32])
+    w[7, 96:128] = 1.5
+    want = orc.quantize(t, w)
+    got = np.empty_like(want)
+    assert L.b200_op_quantize_weights(t, w.ctypes.data, K, N, got.ctypes.data) == 0
+    assert np.array_equal(got, want), (name, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("name,t", TYPES)
 @pytest.mark.parametrize("K,N,Bn", [(4096, 256, 128), (704, 100, 40), (11008, 300, 200), (2048, 513, 512), (64, 16, 129)])
 def test_mul_mat_fast_tcgen05_vs_oracle(L, orc, name, t, K, N, Bn):
     """fused dequant -> tcgen05 GEMM (mmq_tc5.cu), the order-free fast mode: fp16 operands, f32 accumulation in TMEM.  Held to 2e-3 of the row scale
