@@ -48,6 +48,8 @@ struct NeoxLayer {
 };
 struct NeoxParams {
     int n_layer, e, hd, n_head, n_ctx, n_vocab, n_rot, parallel_residual;
+    int gpt2;                                   // GPT-2 (crates/models/gpt2/src/lib.rs:138-329): c_attn rows are [q | k | v] thirds, no RoPE, learned positions wpe, sequential residual
+    const float *wpe;                           // [n_ctx][e] f32 (GPT-2), else nullptr
     QWeight wte, lm_head;
     const float *lnf_g, *lnf_b;
     float kq_scale;

@@ -673,31 +673,42 @@ __global__ void __launch_bounds__(256) ln_pack_kernel(const float *__restrict__ 
     pack_quad(y, pack + (active ? mine >> 3 : 0) * 4, lane, active, q81, off, scale16);
 }
 
-// qkv [3e] (rows per head: q | k | v, bias added) -> RoPE mode 2 on q and k (ggml neox branch, LC/ggml.c:11876-11897: EVERY block of n_rot dims of the head
-// is rotated, pairs (c, c + n_rot/2)), q -> [e], k -> f16 cache row n_past, v -> f16 cache column n_past (gptneox lib.rs:205-247).  One thread per channel.
+// qkv [3e] (bias added) -> q [e], k -> f16 cache row n_past, v -> f16 cache column n_past.  GPT-NeoX (gptneox lib.rs:205-247): rows per head are q | k | v
+// (head stride 3 hd) and q, k get RoPE mode 2 -- the ggml neox branch (LC/ggml.c:11876-11897) rotates EVERY block of n_rot dims of the head, pairs
+// (c, c + n_rot/2).  GPT-2 (gpt2 lib.rs:190-210): the three thirds of the row, no rotation (n_rot = 0).  One thread per channel.
 __global__ void __launch_bounds__(256) neox_rope_store_kernel(const float *__restrict__ qkv, float *__restrict__ q, __half *__restrict__ Kl, __half *__restrict__ Vl,
-                                                              const int *__restrict__ n_past, const float2 *__restrict__ rope_cs, int rope_half, int n_rot, int hd, int e, int n_ctx) {
+                                                              const int *__restrict__ n_past, const float2 *__restrict__ rope_cs, int rope_half, int n_rot, int hd, int e, int n_ctx,
+                                                              int head_stride, int k_off, int v_off) {
     pdl_trigger();
     pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= e) return;
     const int p = __ldcg(n_past);
     const int h = i / hd, c = i - h * hd;
-    const float *base = qkv + (int64_t)h * 3 * hd;
-    const int hb = n_rot / 2, ib = c / n_rot, r = c - ib * n_rot;
-    float qo = __ldcg(base + c), ko = __ldcg(base + hd + c);
-    if (ib < hd / n_rot) {
-        const bool lo = r < hb;
-        const int partner = lo ? c + hb : c - hb;
-        const float2 cs = __ldg(rope_cs + (int64_t)p * rope_half + ib * hb + (lo ? r : r - hb));
-        const float qp = __ldcg(base + partner), kp = __ldcg(base + hd + partner);
-        // x0 = element of the lower half, x1 = upper: out0 = fma(x0, cos, -(x1 sin)), out1 = fma(x0, sin, x1 cos)  (rowops.cu::rope_kernel)
-        qo = lo ? __fmaf_rn(qo, cs.x, -__fmul_rn(qp, cs.y)) : __fmaf_rn(qp, cs.y, __fmul_rn(qo, cs.x));
-        ko = lo ? __fmaf_rn(ko, cs.x, -__fmul_rn(kp, cs.y)) : __fmaf_rn(kp, cs.y, __fmul_rn(ko, cs.x));
+    const float *base = qkv + (int64_t)h * head_stride;
+    float qo = __ldcg(base + c), ko = __ldcg(base + k_off + c);
+    if (n_rot > 0) {
+        const int hb = n_rot / 2, ib = c / n_rot, r = c - ib * n_rot;
+        if (ib < hd / n_rot) {
+            const bool lo = r < hb;
+            const int partner = lo ? c + hb : c - hb;
+            const float2 cs = __ldg(rope_cs + (int64_t)p * rope_half + ib * hb + (lo ? r : r - hb));
+            const float qp = __ldcg(base + partner), kp = __ldcg(base + k_off + partner);
+            // x0 = element of the lower half, x1 = upper: out0 = fma(x0, cos, -(x1 sin)), out1 = fma(x0, sin, x1 cos)  (rowops.cu::rope_kernel)
+            qo = lo ? __fmaf_rn(qo, cs.x, -__fmul_rn(qp, cs.y)) : __fmaf_rn(qp, cs.y, __fmul_rn(qo, cs.x));
+            ko = lo ? __fmaf_rn(ko, cs.x, -__fmul_rn(kp, cs.y)) : __fmaf_rn(kp, cs.y, __fmul_rn(ko, cs.x));
+        }
     }
     q[i] = qo;
     Kl[(int64_t)p * e + i] = __float2half_rn(ko);
-    Vl[(int64_t)i * n_ctx + p] = __float2half_rn(__ldcg(base + 2 * hd + c));
+    Vl[(int64_t)i * n_ctx + p] = __float2half_rn(__ldcg(base + v_off + c));
+}
+
+// GPT-2: inpL = wte[token] + wpe[n_past]  (gpt2 lib.rs:164-172), position read from device memory
+__global__ void __launch_bounds__(256) gpt2_add_pos_kernel(float *__restrict__ x, const float *__restrict__ wpe, const int *__restrict__ n_past, int e) {
+    pdl_wait();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < e) x[i] = __fadd_rn(x[i], __ldg(wpe + (int64_t)__ldcg(n_past) * e + i));
 }
 
 template <int TYPE>
@@ -706,6 +717,7 @@ void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n
     const int e = P.e;
     int n = 0;
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
+    if (P.wpe) { launch_k(gpt2_add_pos_kernel, dim3((e + 255) / 256), dim3(256), 0, st, P.x, P.wpe, (const int *)P.n_past, e); n++; }
     const int nlay = (n_kv_bucket + 63) / 64 * 64;
     const size_t fa_smem = (((size_t)nlay * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (nlay + 32) * 2;
     B200_ASSERT(P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024 && e <= 8192);
@@ -719,7 +731,7 @@ void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n
         MmvArgs A{}; A.xpack = P.xpack_a; A.dst = P.qkv; A.bias = L.bqkv;
         launch_mmv<TYPE, EPI_BIAS>(L.wqkv, A, st); n++;                                                                                      // :199-200
         launch_k(neox_rope_store_kernel, dim3((e + 255) / 256), dim3(256), 0, st, (const float *)P.qkv, P.q, L.K, L.V, (const int *)P.n_past, P.rope_cs, P.rope_half,
-                 P.n_rot, P.hd, e, P.n_ctx); n++;                                                                                             // :205-247
+                 P.gpt2 ? 0 : P.n_rot, P.hd, e, P.n_ctx, P.gpt2 ? P.hd : 3 * P.hd, P.gpt2 ? e : P.hd, P.gpt2 ? 2 * e : 2 * P.hd); n++;               // :205-247
         {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(P.n_head * (P.hd / 32)); cfg.blockDim = dim3(ATH); cfg.dynamicSmemBytes = fa_smem; cfg.stream = st;

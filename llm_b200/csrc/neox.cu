@@ -1,7 +1,9 @@
-// llm_b200/csrc/neox.cu -- native host runtime for GPT-NeoX (include/llm_b200.h: b200_neox_*): model + InferenceSession on the B200.
+// llm_b200/csrc/neox.cu -- native host runtime for GPT-NeoX and GPT-2 (include/llm_b200.h: b200_neox_*): model + InferenceSession on the B200.
 //
 // Mirrors   GptNeoX::new / TensorLoader         crates/models/gptneox/src/lib.rs:36-140
 //           GptNeoX::evaluate (the graph)       crates/models/gptneox/src/lib.rs:156-350   (feed-forward: :487-515)
+//           Gpt2::new / Gpt2::evaluate          crates/models/gpt2/src/lib.rs:43-136, 138-329   (hp.arch == 1: c_attn rows in thirds, no RoPE, learned positions,
+//                                                                                               sequential residual, lm_head optional -> tied to wte)
 //           InferenceSession::compute           crates/llm-base/src/inference_session.rs:114-295
 // Batches (prefill) run node by node on the bit-exact kernels of this directory (LayerNorm, bias adds, RoPE mode 2 on n_rot of the head size, gelu table,
 // exact quantized mat-muls incl. the tcgen05 GEMM, exact f16 attention mat-muls); single tokens run the fused 8-kernels-per-layer schedule of
@@ -24,12 +26,13 @@ struct b200_neox_model {
     char *slab = nullptr;
     size_t slab_bytes = 0, weight_bytes = 0;
     QWeight wte, lm_head;
-    float *lnf_g = nullptr, *lnf_b = nullptr;
+    float *lnf_g = nullptr, *lnf_b = nullptr, *wpe = nullptr;     // wpe: GPT-2 learned positions [n_ctx][e] f32
+    bool gpt2() const { return hp.arch == 1; }
     struct Layer { QWeight wqkv, wdense, wfc, wproj; float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bdense, *bfc, *bproj; };
     std::vector<Layer> layers;
     std::vector<uint8_t> loaded;
     int n_loaded = 0;
-    int n_slots() const { return 4 + 12 * hp.n_layer; }
+    int n_slots() const { return 4 + 12 * hp.n_layer + (gpt2() && hp.has_lm_head ? 1 : 0); }   // GPT-2: slot 3 = wpe, lm_head (if present) last
     struct Slot { QWeight q; float *f = nullptr; int64_t n = 0; bool is_q = false; };
     bool lookup(const char *name, Slot &s, int &id);
 };
@@ -53,6 +56,27 @@ struct b200_neox_session {
 bool b200_neox_model::lookup(const char *name, Slot &s, int &id) {
     const int e = hp.n_embd;
     s = Slot();
+    if (gpt2()) {                                                         // tensor names of crates/models/gpt2/src/lib.rs:59-107
+        if (!strcmp(name, "model/wte")) { s.q = wte; s.is_q = true; id = 0; return true; }
+        if (!strcmp(name, "model/ln_f/g")) { s.f = lnf_g; s.n = e; id = 1; return true; }
+        if (!strcmp(name, "model/ln_f/b")) { s.f = lnf_b; s.n = e; id = 2; return true; }
+        if (!strcmp(name, "model/wpe")) { s.f = wpe; s.n = (int64_t)hp.context_size * e; id = 3; return true; }
+        if (!strcmp(name, "model/lm_head")) { if (!hp.has_lm_head) return false; s.q = lm_head; s.is_q = true; id = 4 + 12 * hp.n_layer; return true; }
+        int il = -1; char sub[96];
+        if (sscanf(name, "model/h%d/%95s", &il, sub) != 2 || il < 0 || il >= hp.n_layer) return false;
+        Layer &L = layers[il];
+        struct { const char *n; QWeight *q; float *f; int64_t len; } tab[] = {
+            {"ln_1/g", nullptr, L.ln1_g, e}, {"ln_1/b", nullptr, L.ln1_b, e}, {"ln_2/g", nullptr, L.ln2_g, e}, {"ln_2/b", nullptr, L.ln2_b, e},
+            {"attn/c_attn/w", &L.wqkv, nullptr, 0}, {"attn/c_attn/b", nullptr, L.bqkv, 3 * (int64_t)e}, {"attn/c_proj/w", &L.wdense, nullptr, 0}, {"attn/c_proj/b", nullptr, L.bdense, e},
+            {"mlp/c_fc/w", &L.wfc, nullptr, 0}, {"mlp/c_fc/b", nullptr, L.bfc, 4 * (int64_t)e}, {"mlp/c_proj/w", &L.wproj, nullptr, 0}, {"mlp/c_proj/b", nullptr, L.bproj, e}};
+        for (int k = 0; k < 12; k++)
+            if (!strcmp(sub, tab[k].n)) {
+                if (tab[k].q) { s.q = *tab[k].q; s.is_q = true; } else { s.f = tab[k].f; s.n = tab[k].len; }
+                id = 4 + 12 * il + k;
+                return true;
+            }
+        return false;
+    }
     if (!strcmp(name, "gpt_neox.embed_in.weight")) { s.q = wte; s.is_q = true; id = 0; return true; }
     if (!strcmp(name, "gpt_neox.final_layer_norm.weight")) { s.f = lnf_g; s.n = e; id = 1; return true; }
     if (!strcmp(name, "gpt_neox.final_layer_norm.bias")) { s.f = lnf_b; s.n = e; id = 2; return true; }
@@ -136,25 +160,30 @@ void forward(b200_neox_session *s, int n, bool all_rows) {
         return;
     }
     const float kq_scale = 1.0f / sqrtf((float)e / (float)n_head);                                                  // :270-273
-    const RopeTable &rope = rope_table(hp.n_rot, 2, 10000.0f, 1.0f, hd, n_ctx);
+    const bool g2 = m->gpt2(), parallel = !g2 && hp.use_parallel_residual;
+    const RopeTable *rope = g2 ? nullptr : &rope_table(hp.n_rot, 2, 10000.0f, 1.0f, hd, n_ctx);
     const int64_t ld3 = 3 * (int64_t)e;
+    // where q / k / v of head h live inside a row of the fused projection: NeoX per head [q | k | v], GPT-2 the three thirds of the row
+    const int64_t hs = g2 ? hd : 3 * hd, koff = g2 ? e : hd, voff = g2 ? 2 * (int64_t)e : 2 * hd;
     get_rows_q(m->wte, s->d_tokens, s->x, n, st); L++;                                                               // :178
+    if (g2) { add_f32(s->x, m->wpe + (size_t)n_past * e, s->x, (int64_t)n * e, (int64_t)n * e, st); L++; }             // gpt2 lib.rs:164-172: + wpe[n_past + i]
     for (int il = 0; il < hp.n_layer; il++) {
         const b200_neox_model::Layer &ly = m->layers[il];
         __half *Kl = s->memory_k + (size_t)il * n_ctx * e, *Vl = s->memory_v + (size_t)il * n_ctx * e;
         layer_norm(s->x, s->cur, ly.ln1_g, ly.ln1_b, e, n, st); L++;                                                  // :192-196
         matmul(s, ly.wqkv, s->cur, s->qkv, ld3, n, st, L);                                                             // :199
         add_f32(s->qkv, ly.bqkv, s->qkv, (int64_t)n * ld3, ld3, st); L++;                                             // :200
-        // q / k of head h live at h*3hd (+hd); RoPE mode 2 in place on both                                              :205-228
-        rope_f32(s->qkv, s->qkv, hd, n_head, n, 3 * hd, ld3, 3 * hd, ld3, n_past, rope, st); L++;
-        rope_f32(s->qkv + hd, s->qkv + hd, hd, n_head, n, 3 * hd, ld3, 3 * hd, ld3, n_past, rope, st); L++;
-        {   // k -> cache rows n_past.., v -> cache columns (transposed)                                                 :231-247
-            StridedDesc sk{{hd, n_head, n, 1}, {4, 3 * (int64_t)hd * 4, ld3 * 4, 0}}, dk{{hd, n_head, n, 1}, {2, (int64_t)hd * 2, (int64_t)e * 2, 0}};
-            cpy_strided(s->qkv + hd, T_F32, sk, Kl + (size_t)n_past * e, T_F16, dk, st); L++;
-            StridedDesc dv{{hd, n_head, n, 1}, {(int64_t)n_ctx * 2, (int64_t)hd * n_ctx * 2, 2, 0}};
-            cpy_strided(s->qkv + 2 * hd, T_F32, sk, Vl + n_past, T_F16, dv, st); L++;
+        if (!g2) {   // RoPE mode 2 in place on q and k                                                                       :205-228
+            rope_f32(s->qkv, s->qkv, hd, n_head, n, hs, ld3, hs, ld3, n_past, *rope, st); L++;
+            rope_f32(s->qkv + koff, s->qkv + koff, hd, n_head, n, hs, ld3, hs, ld3, n_past, *rope, st); L++;
         }
-        mul_mat_f16_exact(Kl, hd, n_kv, n_head, (int64_t)e * 2, (int64_t)hd * 2, s->qkv, n, n_head, ld3 * 4, 3 * (int64_t)hd * 4,
+        {   // k -> cache rows n_past.., v -> cache columns (transposed; GPT-2's v_trans copy of every evaluate is this layout)       :231-247
+            StridedDesc sk{{hd, n_head, n, 1}, {4, hs * 4, ld3 * 4, 0}}, dk{{hd, n_head, n, 1}, {2, (int64_t)hd * 2, (int64_t)e * 2, 0}};
+            cpy_strided(s->qkv + koff, T_F32, sk, Kl + (size_t)n_past * e, T_F16, dk, st); L++;
+            StridedDesc dv{{hd, n_head, n, 1}, {(int64_t)n_ctx * 2, (int64_t)hd * n_ctx * 2, 2, 0}};
+            cpy_strided(s->qkv + voff, T_F32, sk, Vl + n_past, T_F16, dv, st); L++;
+        }
+        mul_mat_f16_exact(Kl, hd, n_kv, n_head, (int64_t)e * 2, (int64_t)hd * 2, s->qkv, n, n_head, ld3 * 4, hs * 4,
                           s->kq, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4, n_past, st); L++;                          // :250-267
         soft_max(s->kq, s->kq, n_kv, (int64_t)n_head * n, n, kq_scale, true, n_past, true, true, st); L++;            // :270-279
         mul_mat_f16_exact(Vl, n_kv, hd, n_head, (int64_t)n_ctx * 2, (int64_t)n_ctx * hd * 2, s->kq, n, n_head, (int64_t)n_kv * 4, (int64_t)n_kv * n * 4,
@@ -162,7 +191,7 @@ void forward(b200_neox_session *s, int n, bool all_rows) {
         matmul(s, ly.wdense, s->cur, s->attn, e, n, st, L);                                                            // :301
         add_f32(s->attn, ly.bdense, s->attn, (int64_t)n * e, e, st); L++;                                             // :302
         const float *ff_in = s->x;
-        if (!hp.use_parallel_residual) { add_f32(s->attn, s->x, s->attn, (int64_t)n * e, (int64_t)n * e, st); L++; ff_in = s->attn; }   // :308-309
+        if (!parallel) { add_f32(s->attn, s->x, s->attn, (int64_t)n * e, (int64_t)n * e, st); L++; ff_in = s->attn; }   // :308-309 / gpt2 :279
         layer_norm(ff_in, s->cur, ly.ln2_g, ly.ln2_b, e, n, st); L++;                                                 // feed_forward :487-493
         matmul(s, ly.wfc, s->cur, s->h4, 4 * (int64_t)e, n, st, L);
         add_f32(s->h4, ly.bfc, s->h4, (int64_t)n * 4 * e, 4 * (int64_t)e, st); L++;
@@ -170,7 +199,7 @@ void forward(b200_neox_session *s, int n, bool all_rows) {
         matmul(s, ly.wproj, s->hact, s->t, e, n, st, L);
         add_f32(s->t, ly.bproj, s->t, (int64_t)n * e, e, st); L++;
         add_f32(s->t, s->attn, s->t, (int64_t)n * e, (int64_t)n * e, st); L++;                                        // parallel: ffn + attn; sequential: ffn + ff_in
-        if (hp.use_parallel_residual) { add_f32(s->t, s->x, s->x, (int64_t)n * e, (int64_t)n * e, st); L++; }        // :324
+        if (parallel) { add_f32(s->t, s->x, s->x, (int64_t)n * e, (int64_t)n * e, st); L++; }        // :324
         else { B200_CHECK(cudaMemcpyAsync(s->x, s->t, (size_t)n * e * 4, cudaMemcpyDeviceToDevice, st)); }
     }
     if (all_rows || n == 1) {
@@ -190,8 +219,8 @@ void forward(b200_neox_session *s, int n, bool all_rows) {
 extern "C" {
 
 b200_neox_model *b200_neox_new(const b200_neox_hparams *hp) {
-    if (!hp || !is_quant(hp->wtype) || hp->n_embd % 64 || hp->n_head <= 0 || hp->n_embd % hp->n_head || hp->n_layer <= 0 || hp->context_size <= 0 ||
-        hp->n_rot <= 0 || hp->n_rot % 2 || hp->n_rot > hp->n_embd / hp->n_head) return nullptr;
+    if (!hp || !is_quant(hp->wtype) || hp->n_embd % 64 || hp->n_head <= 0 || hp->n_embd % hp->n_head || hp->n_layer <= 0 || hp->context_size <= 0 || hp->arch < 0 || hp->arch > 1 ||
+        (hp->arch == 0 && (hp->n_rot <= 0 || hp->n_rot % 2 || hp->n_rot > hp->n_embd / hp->n_head))) return nullptr;
     rt().ensure_init();
     b200_neox_model *m = new b200_neox_model();
     m->hp = *hp;
@@ -205,14 +234,18 @@ b200_neox_model *b200_neox_new(const b200_neox_hparams *hp) {
             if (pass) m->weight_bytes += (size_t)N * (K / QK) * ggml_block_bytes(t);
         };
         auto cf = [&](float *&p, int64_t n) { if (pass) p = (float *)(m->slab + off); off += ((size_t)n * 4 + 255) & ~(size_t)255; };
-        cq(m->wte, e, v); cq(m->lm_head, e, v); cf(m->lnf_g, e); cf(m->lnf_b, e);
+        cq(m->wte, e, v);
+        if (!m->gpt2() || hp->has_lm_head) cq(m->lm_head, e, v);
+        cf(m->lnf_g, e); cf(m->lnf_b, e);
+        if (m->gpt2()) cf(m->wpe, (int64_t)hp->context_size * e);
         for (auto &L : m->layers) {
             cf(L.ln1_g, e); cf(L.ln1_b, e); cf(L.ln2_g, e); cf(L.ln2_b, e); cf(L.bqkv, 3 * e); cf(L.bdense, e); cf(L.bfc, 4 * e); cf(L.bproj, e);
             cq(L.wqkv, e, 3 * e); cq(L.wdense, e, e); cq(L.wfc, e, 4 * e); cq(L.wproj, 4 * e, e);
         }
         if (!pass) { m->slab_bytes = off; B200_CHECK(cudaMalloc(&m->slab, off)); }
     }
-    m->weight_bytes -= (size_t)v * (e / QK) * ggml_block_bytes(t);       // embed_in is gathered from, not streamed
+    if (m->gpt2() && !hp->has_lm_head) m->lm_head = m->wte;              // tied output projection (gpt2 lib.rs:319-320): wte is streamed as the lm_head
+    else m->weight_bytes -= (size_t)v * (e / QK) * ggml_block_bytes(t);  // the embedding table is gathered from, not streamed
     m->loaded.assign(m->n_slots(), 0);
     return m;
 }
@@ -249,7 +282,8 @@ int b200_neox_synthesize(b200_neox_model *m, uint64_t seed) {
     auto g = [&](float *p, int64_t n) { synth_gain(p, n, seed + 0x1000003ull * (++id), st); };
     auto b = [&](float *p, int64_t n) { synth_gain(p, n, seed + 0x1000003ull * (++id), st); scale_shift_f32(p, n, 0.1f, -0.1f, st); };   // 0.01 N(0,1)
     const int e = m->hp.n_embd;
-    q(m->wte); q(m->lm_head); g(m->lnf_g, e); b(m->lnf_b, e);
+    q(m->wte); if (!m->gpt2() || m->hp.has_lm_head) q(m->lm_head); g(m->lnf_g, e); b(m->lnf_b, e);
+    if (m->gpt2()) b(m->wpe, (int64_t)m->hp.context_size * e);
     for (auto &L : m->layers) {
         g(L.ln1_g, e); b(L.ln1_b, e); g(L.ln2_g, e); b(L.ln2_b, e); b(L.bqkv, 3 * e); b(L.bdense, e); b(L.bfc, 4 * e); b(L.bproj, e);
         q(L.wqkv); q(L.wdense); q(L.wfc); q(L.wproj);
@@ -286,7 +320,7 @@ b200_neox_session *b200_neox_start_session(b200_neox_model *m, int32_t n_batch) 
     B200_CHECK(cudaMalloc(&s->qdec, e * 4));
     B200_CHECK(cudaMalloc(&s->xpack_a, (e / QK) * 64)); B200_CHECK(cudaMalloc(&s->xpack_d, (e / QK) * 64)); B200_CHECK(cudaMalloc(&s->xpack_f, (4 * e / QK) * 64));
     B200_CHECK(cudaMalloc(&s->d_n_past, sizeof(int))); B200_CHECK(cudaMallocHost(&s->h_n_past, sizeof(int)));
-    const RopeTable &rt_ = rope_table(hp.n_rot, 2, 10000.0f, 1.0f, m->hd, (int)n_ctx);
+    const RopeTable *rt_ = m->gpt2() ? nullptr : &rope_table(hp.n_rot, 2, 10000.0f, 1.0f, m->hd, (int)n_ctx);
     s->dl.resize(hp.n_layer);
     for (int il = 0; il < hp.n_layer; il++) {
         const b200_neox_model::Layer &L = m->layers[il];
@@ -295,8 +329,8 @@ b200_neox_session *b200_neox_start_session(b200_neox_model *m, int32_t n_batch) 
     }
     NeoxParams &P = s->dp;
     P.n_layer = hp.n_layer; P.e = (int)e; P.hd = m->hd; P.n_head = hp.n_head; P.n_ctx = (int)n_ctx; P.n_vocab = hp.n_vocab; P.n_rot = hp.n_rot;
-    P.parallel_residual = hp.use_parallel_residual; P.wte = m->wte; P.lm_head = m->lm_head; P.lnf_g = m->lnf_g; P.lnf_b = m->lnf_b;
-    P.kq_scale = 1.0f / sqrtf((float)e / (float)hp.n_head); P.rope_cs = rt_.cs; P.rope_half = rt_.half;
+    P.parallel_residual = !m->gpt2() && hp.use_parallel_residual; P.gpt2 = m->gpt2() ? 1 : 0; P.wpe = m->wpe; P.wte = m->wte; P.lm_head = m->lm_head; P.lnf_g = m->lnf_g; P.lnf_b = m->lnf_b;
+    P.kq_scale = 1.0f / sqrtf((float)e / (float)hp.n_head); P.rope_cs = rt_ ? rt_->cs : nullptr; P.rope_half = rt_ ? rt_->half : 0;
     P.lut_gelu = luts().gelu; P.lut_exp = luts().exp; P.token = s->d_tokens; P.n_past = s->d_n_past;
     P.x = s->x; P.qkv = s->qkv; P.q = s->qdec; P.attn_out = s->attn; P.logits = s->logits;
     P.xpack_a = s->xpack_a; P.xpack_d = s->xpack_d; P.xpack_f = s->xpack_f;

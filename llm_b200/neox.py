@@ -14,7 +14,7 @@ from .session import ContextFull
 
 
 class NeoxHparams(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_embd", "n_head", "n_layer", "n_rot", "use_parallel_residual", "wtype", "context_size")]
+    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_embd", "n_head", "n_layer", "n_rot", "use_parallel_residual", "wtype", "context_size", "arch", "has_lm_head")]
 
 
 def _check(rc, what):
@@ -51,13 +51,15 @@ def _bind(L):
 class GptNeoX:
     """hyperparameters: n_vocab, n_ctx, n_embd, n_head, n_layer, n_rot, use_parallel_residual, wtype"""
 
+    ARCH = 0
+
     def __init__(self, hyperparameters: Dict[str, int], tensors: Dict[str, np.ndarray] = None, context_size: int = None, device: int = 0):
         self.L = _bind(_lib.lib())
         _check(self.L.b200_init(device), "b200_init")
         self.hyperparameters = dict(hyperparameters)
         hp = NeoxHparams(n_vocab=hyperparameters["n_vocab"], n_embd=hyperparameters["n_embd"], n_head=hyperparameters["n_head"], n_layer=hyperparameters["n_layer"],
-                         n_rot=hyperparameters["n_rot"], use_parallel_residual=int(hyperparameters.get("use_parallel_residual", 1)), wtype=hyperparameters["wtype"],
-                         context_size=context_size or hyperparameters["n_ctx"])
+                         n_rot=int(hyperparameters.get("n_rot", 0)), use_parallel_residual=int(hyperparameters.get("use_parallel_residual", 1)), wtype=hyperparameters["wtype"],
+                         context_size=context_size or hyperparameters["n_ctx"], arch=self.ARCH, has_lm_head=int(bool(tensors) and "model/lm_head" in tensors))
         self._m = self.L.b200_neox_new(C.byref(hp))
         if not self._m:
             raise ValueError(f"b200_neox_new rejected {hyperparameters}")
@@ -86,6 +88,13 @@ class GptNeoX:
             self.close()
         except Exception:
             pass
+
+
+class Gpt2(GptNeoX):
+    """KnownModel for GPT-2 (crates/models/gpt2/src/lib.rs): hyperparameters n_vocab, n_ctx, n_embd, n_head, n_layer, wtype; tensors "model/wte",
+    "model/wpe" (f32), "model/ln_f/g|b", optional "model/lm_head", "model/hN/{ln_1,ln_2}/{g,b}", "model/hN/attn/{c_attn,c_proj}/{w,b}",
+    "model/hN/mlp/{c_fc,c_proj}/{w,b}".  context_size is the model's n_ctx (the rows of wpe)."""
+    ARCH = 1
 
 
 class NeoxSession:

@@ -68,3 +68,44 @@ def test_neox_20b_geometry_two_layers(orc, name):
     for i in range(254, 259):
         check(s.evaluate(toks[i:i + 1], all_logits=True), mr.eval(toks[i:i + 1]), f"20b-2l decode {i} (bucket edge)")
     s.close(); m.close(); mr.close()
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q5_1", "q8_0"])
+@pytest.mark.parametrize("lm_head", [False, True])
+def test_gpt2_native_vs_reference(orc, name, lm_head):
+    """GPT-2 (BASELINE.json configs[0] family) on the same native runtime: learned positions, c_attn in thirds, no RoPE, sequential residual, output
+    projection tied to wte or a separate lm_head -- logits bit-identical to the reference's GPT-2 graph on its own ggml CPU build"""
+    from llm_b200.neox import Gpt2
+    t = B.QUANT_TYPES[name]
+    cfg = dict(n_vocab=320, n_ctx=128, n_embd=256, n_head=4, n_layer=2)
+    hp, tens = synth.make_gpt2(cfg, t, orc.quantize, lm_head=lm_head)
+    toks = synth.make_tokens(hp, 60)
+    if not B.have_ref("ref"):
+        pytest.skip("oracle/_ref/libggml_ref.so not built")
+    mr = B.RefLib("ref").gpt2(hp, tens, n_threads=8, n_batch=64)
+    m = Gpt2(hp, tens)
+    s = m.start_session(64)
+    check(s.evaluate(toks[:20], all_logits=True), mr.eval(toks[:20]), "gpt2 prefill 20")
+    for i in range(20, 28):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mr.eval(toks[i:i + 1]), f"gpt2 decode {i}")
+        assert s.last_launches == 8 * hp["n_layer"] + 4, ("fused decode schedule not used", s.last_launches)
+    check(s.evaluate(toks[28:45], all_logits=True), mr.eval(toks[28:45]), "gpt2 batch 17 after decode")
+    check(s.evaluate(toks[45:46], all_logits=True), mr.eval(toks[45:46]), "gpt2 decode after batch")
+    s.close(); m.close(); mr.close()
+
+
+@pytest.mark.slow
+def test_gpt2_117m_geometry(orc):
+    """BASELINE.json configs[0]: GPT-2 117M geometry (768 / 12 heads / 12 layers / vocab 50257 / n_ctx 1024) Q4_0, 32-token prompt + 4 decode steps"""
+    from llm_b200.neox import Gpt2
+    hp, tens = synth.make_gpt2(dict(synth.GPT2_CONFIGS["gpt2-117m"], n_layer=3), B.Q4_0, orc.quantize)
+    toks = synth.make_tokens(hp, 40)
+    if not B.have_ref("ref"):
+        pytest.skip("oracle/_ref/libggml_ref.so not built")
+    mr = B.RefLib("ref").gpt2(hp, tens, n_threads=8, n_batch=64)
+    m = Gpt2(hp, tens)
+    s = m.start_session(64)
+    check(s.evaluate(toks[:32], all_logits=True), mr.eval(toks[:32]), "117m prefill 32")
+    for i in range(32, 36):
+        check(s.evaluate(toks[i:i + 1], all_logits=True), mr.eval(toks[i:i + 1]), f"117m decode {i}")
+    s.close(); m.close(); mr.close()
