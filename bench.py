@@ -200,6 +200,49 @@ def cpu_reference(metric, steps, warmup, log=lambda *a: None, weights=None, gpu=
     return out
 
 
+def cuda_reference(args, steps, warmup, log):
+    """Prior art on the same box: the reference's own CUDA backend -- LC/ggml-cuda.cu compiled UNMODIFIED for sm_100 with cuBLAS (oracle/Makefile `refcuda`),
+    driven by the reference's ggml graph executor through the LLaMA graph exactly as llm-base does with ModelParameters::use_gpu (all layers offloaded):
+    dequantize + cuBLAS for batches (LC/ggml-cuda.cu:3121-3160), mul_mat_vec_q / dp4a for single tokens (:1807-1843).  Timed on the host clock around
+    evaluate (the executor synchronises per node).  Checker-side code; nothing of it is linked into the product."""
+    from oracle import bindings as B
+    from oracle import synth
+    if not B.have_ref("refcuda"):
+        return {"impl": "reference-cuda", "unavailable": "oracle/_ref/libggml_refcuda.so not built (make -C oracle refcuda needs /root/reference and nvcc)"}
+    hp = dict(synth.CONFIGS["7b"], n_layer=args.layers, n_ctx=N_PAST + 64, wtype=B.Q4_0)
+    hp, weights = synth.make_llama_random_blocks(hp, B.Q4_0)
+    ref = B.RefLib("refcuda")
+    toks = synth.make_tokens(hp, N_PAST + 1)
+    best = None
+    for nt in (1, 4, 8):
+        m = ref.llama(hp, weights, use_gpu=1, n_threads=nt, n_batch=N_PAST)
+        m.eval(toks[:N_PAST])                                          # warm-up (cuBLAS handles, pools)
+        pf = []
+        for _ in range(3):
+            m.set_n_past(0)
+            t0 = time.time(); m.eval(toks[:N_PAST]); pf.append(time.time() - t0)
+        logits = np.empty((1, hp["n_vocab"]), np.float32)
+        ts = []
+        for i in range(warmup + steps):
+            m.set_n_past(N_PAST)
+            t0 = time.time(); m.eval_into(toks[N_PAST:N_PAST + 1], logits); ts.append(time.time() - t0)
+        t_tok, t_pf = statistics.median(ts[warmup:]), min(pf)
+        log(f"reference CUDA backend, {nt} host thread(s): decode {t_tok * 1e3:.2f} ms/token ({1 / t_tok:.0f} tok/s), prefill@512 {t_pf * 1e3:.1f} ms ({N_PAST / t_pf:.0f} tok/s)")
+        if best is None or t_tok < best[0]:
+            best = (t_tok, t_pf, nt)
+        m.close()
+    prefill_metric = args.metric == "prefill"
+    val = N_PAST / best[1] if prefill_metric else 1.0 / best[0]
+    return {"impl": "reference-cuda", "metric": METRIC_PREFILL if prefill_metric else METRIC, "value": val, "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": (best[1] if prefill_metric else best[0]) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "reference CUDA kernels: dp4a mat-vec on Q8_1 activations (decode), dequantize -> cuBLAS (prefill)", "data": "synthetic",
+            "config": {"workload": "LLaMA-7B Q4_0, the reference's own CUDA backend (LC/ggml-cuda.cu recompiled for sm_100) under its ggml graph executor", "n_layer": args.layers,
+                       "host_threads": best[2]},
+            "decode_tokens_per_s": 1.0 / best[0], "prefill_tokens_per_s": N_PAST / best[1], "prefill_ms": best[1] * 1e3,
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 4 * (N_PAST if prefill_metric else 1), "d2h_bytes_per_step": 4 * hp["n_vocab"] * (N_PAST if prefill_metric else 1)},
+            "note": "not bit-exact with the reference's CPU path (its own CUDA kernels use a different summation order); context for the product's numbers, not a parity target"}
+
+
 MODELS = {"7b-q4_0": dict(HP_7B), "13b-q5_1": dict(n_vocab=32000, n_embd=5120, n_head=40, n_head_kv=40, n_layer=40, n_rot=128, n_ff=13824, wtype=7)}
 BLK_BYTES = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
 
@@ -345,7 +388,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"],
+                    help="reference = the reference's ggml CPU path; reference-cuda = the reference's own CUDA backend (LC/ggml-cuda.cu recompiled for sm_100, oracle/_ref) on this GPU")
     ap.add_argument("--metric", default="decode", choices=["decode", "prefill"], help="which half of BASELINE.json's metric the JSON line reports")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is NOT the benchmark config")
@@ -370,6 +414,10 @@ def main():
                 else "LLaMA-7B Q4_0 decode batch=1 n_past=512 (BASELINE.json configs[1])")
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
+    if args.impl == "reference-cuda":
+        if rank == 0:
+            emit(cuda_reference(args, steps, warmup, log))
+        return
     if args.impl == "reference":
         if rank != 0:
             return
