@@ -67,7 +67,7 @@ template <int TYPE>
 __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, const QWeight w, const float4 *__restrict__ xdt,
                                                                    float *__restrict__ dst, int64_t ldd, int64_t B, const float *__restrict__ addend, int64_t lda) {
     using T = Tc<TYPE>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;                     // 128B-swizzled tiles need 1024-byte alignment
     uint8_t *const sptr = smem_raw + (sbase - smem_u32(smem_raw));
     const uint32_t sA = sbase, sB = sbase + NST * A_STAGE, sW = sB + NST * B_STAGE, sX = sW + DWR * TN * 8, sBar = sX + XR * X_STAGE;
@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
             uint32_t col_off[4];
 #pragma unroll
             for (int l = 0; l < 4; l++) col_off[l] = (uint32_t)((r >> 1) * B_SBO + (l >> 1) * B_LBO + (4 * (r & 1) + l) * 16 + (l & 1) * 8);
-            auto expand = [&](const WRaw &x, int slot, int j, int blk) {
+            int wslot = 0;                                                                             // scale-ring slot of the block being expanded
+            auto expand = [&](const WRaw &x, int slot, int j) {
                 uint8_t *out = pB + slot * B_STAGE + (j * 2 + h) * B_HALF;
                 const uint32_t qw[4] = {x.q.x, x.q.y, x.q.z, x.q.w};
 #pragma unroll
@@ -177,11 +178,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
                     f.y = bytes_to_half2(v, 0x4342u, T::OFF);
                     *(uint2 *)(out + col_off[l]) = f;
                 }
-                if (h == 0) {
-                    float2 dm;
-                    if (T::MIN) { __half2 hh; memcpy(&hh, &x.dm, 4); dm = make_float2(__low2float(hh), __high2float(hh)); }
-                    else dm = make_float2(__half2float(__ushort_as_half((unsigned short)x.dm)), 0.f);
-                    pW[(blk % DWR) * TN + r] = dm;
+                if (h == 0) {                                                                          // f32 scales, two planes: d[DWR][32] | m[DWR][32]
+                    float *pd = (float *)pW;
+                    if (T::MIN) { __half2 hh; memcpy(&hh, &x.dm, 4); pd[wslot * TN + r] = __low2float(hh); pd[DWR * TN + wslot * TN + r] = __high2float(hh); }
+                    else pd[wslot * TN + r] = __half2float(__ushort_as_half((unsigned short)x.dm));
                 }
             };
             WRaw c0[2], c1[2];                                                                     // two stages in flight
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
                     const int slot = s2 % NST; const uint32_t par = (s2 / NST) & 1;
                     mbar_wait(bar_empty(slot), par ^ 1, dead);
                     WRaw *cur = u ? c1 : c0;
-                    expand(cur[0], slot, 0, 2 * s2); expand(cur[1], slot, 1, 2 * s2 + 1);
+                    expand(cur[0], slot, 0); if (++wslot == DWR) wslot = 0;
+                    expand(cur[1], slot, 1); if (++wslot == DWR) wslot = 0;
                     if (s2 + 2 < nstage) { cur[0] = fetch(2 * (s2 + 2)); cur[1] = fetch(2 * (s2 + 2) + 1); }
                     fence_proxy_async_smem();
                     mbar_arrive(bar_b_full(slot));
@@ -218,29 +219,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
 #pragma unroll
             for (int p = 0; p < 4; p++) acc[r][p] = make_float2(0.f, 0.f); }
 
-        uint32_t dA[32], dB[32];                                                                   // TMEM staging, double-buffered: {lanes 0-3 | lanes 4-7} x 4 rows
-        float4 wA[2], wB[2];                                                                       // {d, m} of the chunk's 4 rows
-        auto issue = [&](int blk, int c, uint32_t (&d)[32], float4 (&wv)[2]) {
+        // chunk = 8 rows x 4 lanes of ONE half-block = one 32-column tcgen05.ld (the wide loads use the TMEM read port best: profiles/r02_notes.md);
+        // order per block: (rows 0-7, lanes 0-3), (rows 0-7, lanes 4-7), (rows 8-15, lanes 0-3), (rows 8-15, lanes 4-7)
+        uint32_t dA[32], dB[32];                                                                   // TMEM staging, double-buffered
+        float4 wd[2], wm[2];                                                                       // d (and m) of the chunk pair's 8 rows
+        float sc[8];                                                                               // d_w * d_x of those rows (shared by the two halves)
+        const float *pWd = (const float *)pW, *pWm = pWd + DWR * TN;                               // scale ring as two planes: d[DWR][32] | m[DWR][32]
+        int wslot = 0, xslot = 0;                                                                  // ring positions of the block / stage being LOADED next
+        auto issue = [&](int blk, int c, uint32_t (&d)[32]) {                                     // c = 0..3 as listed above
             const int buf = blk & 1;
             if (c == 0) { mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead); tc_fence_after(); }
-            tmem_ld_x16(t_lane + buf * 256 + c * 16, *(uint32_t(*)[16])&d[0]);
-            tmem_ld_x16(t_lane + buf * 256 + 128 + c * 16, *(uint32_t(*)[16])&d[16]);
-            const float4 *wrow = (const float4 *)(pW + (blk % DWR) * TN + ch * 16 + c * 4);
-            wv[0] = wrow[0]; wv[1] = wrow[1];
+            tmem_ld_x32(t_lane + buf * 256 + (c & 1) * 128 + (c >> 1) * 32, d);
         };
-        auto compute = [&](int c, const uint32_t (&d)[32], const float4 (&wv)[2], float dx, float sx) {
+        auto load_w = [&](int slot, int c2) {                                                     // rows 8 c2 .. 8 c2 + 7 of the block in ring slot `slot`
+            const float4 *pd = (const float4 *)(pWd + slot * TN + ch * 16 + c2 * 8);
+            wd[0] = pd[0]; wd[1] = pd[1];
+            if (T::MIN) { const float4 *pm = (const float4 *)(pWm + slot * TN + ch * 16 + c2 * 8); wm[0] = pm[0]; wm[1] = pm[1]; }
+        };
+        auto compute = [&](int c, const uint32_t (&d)[32], float dx, float sx) {
+            const int h = c & 1, r0 = (c >> 1) * 8;
+            if (h == 0) {
+                const float dws[8] = {wd[0].x, wd[0].y, wd[0].z, wd[0].w, wd[1].x, wd[1].y, wd[1].z, wd[1].w};
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
-                const int r = c * 4 + rr;
-                const float dw = rr == 0 ? wv[0].x : rr == 1 ? wv[0].z : rr == 2 ? wv[1].x : wv[1].z;
-                const float mw = rr == 0 ? wv[0].y : rr == 1 ? wv[0].w : rr == 2 ? wv[1].y : wv[1].w;
-                const float s = __fmul_rn(dw, dx);
-                const float2 s2 = make_float2(s, s);
-                acc[r][0] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 0]), __uint_as_float(d[rr * 4 + 1])), acc[r][0]);
-                acc[r][1] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 2]), __uint_as_float(d[rr * 4 + 3])), acc[r][1]);
-                acc[r][2] = ffma2(s2, make_float2(__uint_as_float(d[16 + rr * 4 + 0]), __uint_as_float(d[16 + rr * 4 + 1])), acc[r][2]);
-                acc[r][3] = ffma2(s2, make_float2(__uint_as_float(d[16 + rr * 4 + 2]), __uint_as_float(d[16 + rr * 4 + 3])), acc[r][3]);
-                if (T::MIN) summs[r] = __fmaf_rn(mw, sx, summs[r]);
+                for (int rr = 0; rr < 8; rr++) sc[rr] = __fmul_rn(dws[rr], dx);
+                if (T::MIN) {
+                    const float mws[8] = {wm[0].x, wm[0].y, wm[0].z, wm[0].w, wm[1].x, wm[1].y, wm[1].z, wm[1].w};
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) summs[r0 + rr] = __fmaf_rn(mws[rr], sx, summs[r0 + rr]);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const float2 s2 = make_float2(sc[rr], sc[rr]);
+                acc[r0 + rr][2 * h] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 0]), __uint_as_float(d[rr * 4 + 1])), acc[r0 + rr][2 * h]);
+                acc[r0 + rr][2 * h + 1] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 2]), __uint_as_float(d[rr * 4 + 3])), acc[r0 + rr][2 * h + 1]);
             }
         };
         auto release = [&](int blk) {                                                              // every column of the block's buffer is in registers
@@ -248,21 +260,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_t_empty(blk & 1));
         };
+        auto next_w = [&]() { int s0 = wslot; if (++wslot == DWR) wslot = 0; return s0; };
 
-        if (nstage > 0) issue(0, 0, dA, wA);
+        int ws = 0;                                                                                // ring slot of the block being computed
+        if (nstage > 0) { issue(0, 0, dA); ws = next_w(); load_w(ws, 0); }
         for (int st = 0; st < nstage; st++) {
             // the scales of this stage (landed with the stage's activations, before its MMAs ran)
-            const float4 xd = pX[(st % XR) * TM + tok];
+            const float4 xd = pX[xslot * TM + tok];
+            if (++xslot == XR) xslot = 0;
             const bool more = st + 1 < nstage;
             const int b0 = 2 * st, b1 = 2 * st + 1;
-            tc_wait_ld(); issue(b0, 1, dB, wB); compute(0, dA, wA, xd.x, xd.y);
-            tc_wait_ld(); issue(b0, 2, dA, wA); compute(1, dB, wB, xd.x, xd.y);
-            tc_wait_ld(); issue(b0, 3, dB, wB); compute(2, dA, wA, xd.x, xd.y);
-            tc_wait_ld(); release(b0); issue(b1, 0, dA, wA); compute(3, dB, wB, xd.x, xd.y);
-            tc_wait_ld(); issue(b1, 1, dB, wB); compute(0, dA, wA, xd.z, xd.w);
-            tc_wait_ld(); issue(b1, 2, dA, wA); compute(1, dB, wB, xd.z, xd.w);
-            tc_wait_ld(); issue(b1, 3, dB, wB); compute(2, dA, wA, xd.z, xd.w);
-            tc_wait_ld(); release(b1); if (more) issue(b1 + 1, 0, dA, wA); compute(3, dB, wB, xd.z, xd.w);
+            // the weight scales of rows 8-15 are fetched once compute(0) has turned rows 0-7's into sc[]; the next block's only after its tmem_full wait
+            // (the expander wrote them before the MMAs the barrier reports)
+            tc_wait_ld(); issue(b0, 1, dB); compute(0, dA, xd.x, xd.y); load_w(ws, 1);
+            tc_wait_ld(); issue(b0, 2, dA); compute(1, dB, xd.x, xd.y);
+            tc_wait_ld(); issue(b0, 3, dB); compute(2, dA, xd.x, xd.y);
+            tc_wait_ld(); release(b0); issue(b1, 0, dA); ws = next_w(); load_w(ws, 0); compute(3, dB, xd.x, xd.y);
+            tc_wait_ld(); issue(b1, 1, dB); compute(0, dA, xd.z, xd.w); load_w(ws, 1);
+            tc_wait_ld(); issue(b1, 2, dA); compute(1, dB, xd.z, xd.w);
+            tc_wait_ld(); issue(b1, 3, dB); compute(2, dA, xd.z, xd.w);
+            tc_wait_ld(); release(b1); if (more) { issue(b1 + 1, 0, dA); ws = next_w(); load_w(ws, 0); } compute(3, dB, xd.z, xd.w);
         }
         // hsum_float_8 (LC/ggml.c:608-616): ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), then + summs
         if (m < B) {

@@ -10,9 +10,9 @@
 // CTA = 128 tokens (M, TMEM lanes) x 256 weight rows (N, TMEM columns), K stepped 64 elements per pipeline stage:
 //   warp 0      TMA producer: activations f16 [128 tokens x 64] (128B swizzle), one cp.async.bulk.tensor per stage
 //   warp 1      MMA issuer: 4 x tcgen05.mma.kind::f16 (M128 N256 K16) per stage, accumulate in TMEM; tcgen05.commit frees the stage
-//   warps 8-15  dequant: thread = weight row; packed nibbles (+ fifth bits) -> f16 via the 0x6400 magic, one HFMA2 per pair applies d (and m), written as the
+//   warps 6-21  dequant: thread = (weight row, block of the stage); packed nibbles (+ fifth bits) -> f16 via the 0x6400 magic, one HFMA2 per pair applies d (and m), written as the
 //               128B-swizzled K-major B operand (the scale d is the row-block's fp16 scalar in a register, broadcast by the HFMA2 operand)
-//   warps 4-7   epilogue: tcgen05.ld 32 columns at a time, f32 stores (+ addend)
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, f32 stores (+ addend)
 #include <string.h>
 
 #include "kernels.cuh"
@@ -26,7 +26,8 @@ using namespace tc5;
 
 constexpr int FM = 128, FN = 256, FST = 4;
 constexpr int FA = FM * 128, FB = FN * 128;                       // bytes per stage: [rows][64 f16] = 128-byte rows, swizzled
-constexpr int FTHREADS = 512;
+constexpr int FTHREADS = 704;                                    // TMA + MMA + 4 epilogue + 16 dequant warps (one (row, block) per thread and stage: the dequant
+                                                                  // is ~2.7 instructions per weight and needs the warps to hide its own latencies, profiles/r02_notes.md)
 constexpr int FSMEM = 1024 + FST * (FA + FB) + 256;
 
 template <int TYPE> struct Fq {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) mm_fast_tc5_kernel(const __grid_c
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap_x);
-        for (int s = 0; s < FST; s++) { mbar_init(bar_a(s), 1); mbar_init(bar_b(s), 256); mbar_init(bar_e(s), 1); }
+        for (int s = 0; s < FST; s++) { mbar_init(bar_a(s), 1); mbar_init(bar_b(s), 512); mbar_init(bar_e(s), 1); }
         mbar_init(bar_done, 1);
         fence_barrier_init();
     }
@@ -106,9 +107,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) mm_fast_tc5_kernel(const __grid_c
             }
             tc_commit(bar_done);
         }
-    } else if (warp >= 8) {
-        // ================= dequant: thread = weight row of the tile =================
-        const int r = tid - 256;
+    } else if (warp >= 6) {
+        // ================= dequant: thread = (weight row of the tile, block j of the stage) =================
+        const int r = (tid - 192) & 255, j = (tid - 192) >> 8;
         const int64_t n = n_base + r < w.N ? n_base + r : w.N - 1;
         const uint8_t *q_ptr = w.qs + (size_t)n * nb * T::QS;
         const uint8_t *d_ptr = (const uint8_t *)w.dm + (size_t)n * nb * T::DM;
@@ -146,25 +147,27 @@ __global__ void __launch_bounds__(FTHREADS, 1) mm_fast_tc5_kernel(const __grid_c
                 *(uint4 *)(row + (((uint32_t)(4 * j + c) ^ sw) << 4)) = f;
             }
         };
-        Raw c0[2], c1[2];
-        if (nstage > 0) { c0[0] = fetch(0); c0[1] = fetch(1); }
-        if (nstage > 1) { c1[0] = fetch(2); c1[1] = fetch(3); }
-        for (int st = 0; st < nstage; st += 2) {
+        Raw c0, c1, c2, c3;                                                                        // four stages in flight
+        if (nstage > 0) c0 = fetch(j);
+        if (nstage > 1) c1 = fetch(2 + j);
+        if (nstage > 2) c2 = fetch(4 + j);
+        if (nstage > 3) c3 = fetch(6 + j);
+        for (int st = 0; st < nstage; st += 4) {
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < 4; u++) {
                 const int s2 = st + u;
                 if (s2 >= nstage) break;
                 const int slot = s2 % FST; const uint32_t par = (s2 / FST) & 1;
                 mbar_wait(bar_e(slot), par ^ 1, dead);
-                Raw *cur = u ? c1 : c0;
-                expand(cur[0], slot, 0); expand(cur[1], slot, 1);
-                if (s2 + 2 < nstage) { cur[0] = fetch(2 * (s2 + 2)); cur[1] = fetch(2 * (s2 + 2) + 1); }
+                Raw &cur = u == 0 ? c0 : u == 1 ? c1 : u == 2 ? c2 : c3;
+                expand(cur, slot, j);
+                if (s2 + 4 < nstage) cur = fetch(2 * (s2 + 4) + j);
                 fence_proxy_async_smem();
                 mbar_arrive(bar_b(slot));
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue =================
+    } else if (warp >= 2) {
+        // ================= epilogue (4 consecutive warps cover the 4 TMEM lane quarters) =================
         const int q = warp & 3;
         const int64_t m = m_base + q * 32 + lane;
         mbar_wait(bar_done, 0, dead);
