@@ -35,6 +35,7 @@ struct DecodeParams {
     // n_vocab = local rows of the lm_head) except e = the full n_embd; e_loc = n_embd / G (q rows, rows of wo / w2 owned here)
     TpCtx tp;
     int e_loc = 0, head0 = 0;           // first global head of this rank
+    int n_vocab_full = 0;               // rows of the whole lm_head (the gathered logits)
     int64_t row0_e = 0, row0_w13 = 0, row0_v = 0;   // first row of this rank in the full wo / w2 output, the interleaved [w1|w3] rows, the lm_head
     unsigned int *bar;                  // [0] arrival count, [1] generation
     unsigned long long *prof;   /* graph schedule: 3 x B200_PROF_SLOTS timeline slots (begin | end | prologue done) */           // optional: %globaltimer stamps of CTA 0 at phase boundaries (debug / tuning), 128 slots

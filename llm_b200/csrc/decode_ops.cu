@@ -79,7 +79,15 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
     pdl_wait();
-    if (T.world > 1) { if (tid == 0) tp_wait_thread(T, S); __syncthreads(); }     // tensor-parallel: every rank's slice of the row has landed
+    const bool tp = T.world > 1;                               // tensor-parallel: the row is an array of {value, tag} units filled by every rank (tp.cuh)
+    const unsigned tag = tp ? tp_tag(T, S.in_v) : 0u;
+    auto ld4 = [&](int i) {
+        if (!tp) return __ldcg((const float4 *)x + i);
+        float4 v;
+        v.x = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 0, tag); v.y = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 1, tag);
+        v.z = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 2, tag); v.w = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 3, tag);
+        return v;
+    };
     prof_begin(prof);
     // this CTA's 32 blocks are float4s [blockIdx.x * 256, +256) of the row: thread tid packs float4 blockIdx.x * 256 + tid, which is also
     // one of the values it sums -- the row is read once, all loads (row and gains) are in flight before the first use (one L2 round trip)
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     for (int i0 = tid; i0 < nv; i0 += 256 * U) {
         float4 v[U];
 #pragma unroll
-        for (int k = 0; k < U; k++) { const int i = i0 + 256 * k; v[k] = i < nv ? __ldcg((const float4 *)x + i) : make_float4(0.f, 0.f, 0.f, 0.f); }   // written by a predecessor: L2-coherent load
+        for (int k = 0; k < U; k++) { const int i = i0 + 256 * k; v[k] = i < nv ? ld4(i) : make_float4(0.f, 0.f, 0.f, 0.f); }   // written by a predecessor: L2-coherent load
 #pragma unroll
         for (int k = 0; k < U; k++) {
             if (i0 + 256 * k == mine) xv = v[k];
@@ -130,7 +138,7 @@ struct MmvArgs {
     // EPI_BIAS: dst = ((W x + bias) [+ add1]) [+ add2] in that order (ggml_add nodes of gptneox lib.rs:200,302,308-325); EPI_GELU: gelu(W x + bias) quantized
     const float *bias, *add1, *add2; const uint16_t *lut_gelu;
     // tensor-parallel decode (tp.cuh): this rank owns rows [row0, row0 + w.N) of the full matrix; results go to buffer dst_buf of every rank
-    TpCtx tp; TpSync ts; int64_t row0; int dst_buf;
+    TpCtx tp; TpSync ts; int64_t row0;
 };
 
 template <int TYPE, int EPI>
@@ -151,9 +159,13 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         return;
     }
     pdl_wait();
-    if (A.tp.world > 1 && A.ts.wait_buf >= 0) { if (tid == 0) tp_wait_thread(A.tp, A.ts); compute_sync(); }   // the gathered input records are complete
-    for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (A.tp.world > 1 && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
+        const unsigned tag = tp_tag(A.tp, A.ts.in_v);
+        for (int i = tid; i < (int)w.nb * 16; i += SCOMPUTE) ((uint32_t *)sx)[i] = tp_get(A.tp, A.ts.in_buf, i, tag);
+    } else {
+        for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
     float *stash = (float *)(sx + (size_t)w.nb * 4);      // 64 floats behind the records (EPI_SILU)
     compute_sync();
     prof_ready(A.prof);
@@ -162,8 +174,10 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
             if ((tid & 3) != 0 || row >= w.N) return;
             const int64_t g = A.row0 + row;                      // row of the full matrix (row0 = 0 on a single GPU)
-            const float out = A.addend ? __fadd_rn(v, __ldcg(A.addend + g)) : v;
-            if (A.tp.world > 1) tp_store_f32(A.tp, A.dst_buf, g, out); else A.dst[g] = out;
+            if (A.tp.world > 1) {                                // addend: this rank's own slice of the gathered vector; result: to every rank
+                const float out = A.ts.add_buf >= 0 ? __fadd_rn(v, tp_get_f32(A.tp, A.ts.add_buf, g, tp_tag(A.tp, A.ts.add_v))) : v;
+                tp_put_f32(A.tp, A.ts.out_buf, g, out, tp_tag(A.tp, A.ts.out_v));
+            } else A.dst[g] = A.addend ? __fadd_rn(v, __ldcg(A.addend + g)) : v;
         }, 1, A.prof);
         if (EPI == EPI_LOGITS && blockIdx.x == 0 && tid == 0) *A.n_past_inc = *A.n_past_inc + 1;
     } else if (EPI == EPI_QKV) {
@@ -218,13 +232,12 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
                 const int64_t blk = (A.row0 >> 6) + (row >> 6);     // block of w2's input (row0 counts this rank's interleaved w1|w3 rows)
                 int4 rec;
                 if (pack_quad_rec(hm, lane, lane < 8, A.q81, A.off, A.scale16, rec)) {
-                    if (A.tp.world > 1) tp_store_rec(A.tp, TPB_XF, blk * 4 + (lane & 7), rec); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
+                    if (A.tp.world > 1) tp_put_rec(A.tp, TPB_XF, blk * 4 + (lane & 7), rec, tp_tag(A.tp, A.ts.out_v)); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
                 }
             }
             compute_sync();
         }, G, A.prof);
     }
-    if (A.tp.world > 1 && A.ts.sig_buf >= 0) { compute_sync(); if (tid == 0) tp_signal_thread(A.tp, A.ts, gridDim.x); }
     pdl_trigger();                                              // late: this CTA has consumed its last tile
     prof_end(A.prof);
 }
@@ -502,10 +515,9 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
         int4 rec;
         const int64_t blk = (int64_t)(((head0 + h) * hd + c0) / QK);       // block of wo's input: heads are global (head0 = first head of this rank)
         if (pack_quad_rec(((const float4 *)stash)[lane & 7], lane, lane < 8, q81, off, scale16, rec)) {
-            if (T.world > 1) tp_store_rec(T, TPB_XD, blk * 4 + (lane & 7), rec); else xpack_out[blk * 4 + (lane & 7)] = rec;
+            if (T.world > 1) tp_put_rec(T, TPB_XD, blk * 4 + (lane & 7), rec, tp_tag(T, S.out_v)); else xpack_out[blk * 4 + (lane & 7)] = rec;
         }
     }
-    if (T.world > 1) { __syncthreads(); if (tid == 0) tp_signal_thread(T, S, gridDim.x); }
     prof_end(prof);
 }
 
@@ -548,10 +560,23 @@ void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
     launch_k<1>(mmv_fused_kernel<TYPE, EPI>, dim3((unsigned)(groups < slots ? groups : slots)), dim3(STHREADS), (size_t)smem_of(nst), st, w, A);
 }
 
-// last node of a tensor-parallel token: every rank's logits slice has landed here; then the epoch moves on (tp.cuh)
-__global__ void tp_fence_kernel(const TpCtx T, const TpSync S) {
+// tensor-parallel helpers (tp.cuh).  spread: the embedding row every rank computed for itself -> the X exchange buffer's unit form (stamp 0);
+// collect: the gathered logits units -> the plain f32 logits array the host reads; bump: the token is complete, the epoch moves on.
+__global__ void __launch_bounds__(256) tp_spread_kernel(const float *__restrict__ x, int n, const TpCtx T) {
     pdl_wait();
-    if (threadIdx.x == 0) { tp_wait_thread(T, S); __threadfence(); *T.epoch = *(volatile unsigned *)T.epoch + 1; }
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint2 *dst = (uint2 *)(T.peer[T.rank] + T.off[TPB_X]) + i;
+    *dst = make_uint2(__float_as_uint(__ldcg(x + i)), tp_tag(T, 0));
+}
+__global__ void __launch_bounds__(256) tp_collect_kernel(float *__restrict__ logits, int n, const TpCtx T) {
+    pdl_wait();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) logits[i] = tp_get_f32(T, TPB_LOGITS, i, tp_tag(T, 0));
+}
+__global__ void tp_bump_kernel(const TpCtx T) {
+    pdl_wait();
+    if (threadIdx.x == 0) *T.epoch = *(volatile unsigned *)T.epoch + 1;
 }
 
 template <int TYPE>
@@ -561,12 +586,16 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     const TpCtx &T = P.tp;
     const bool tp = T.world > 1;
     const int e_loc = tp ? P.e_loc : e;
-    auto ts = [&](int wait_buf, unsigned wait_v, int sig_buf, unsigned sig_v, int site) {
-        TpSync S; S.wait_buf = tp ? wait_buf : -1; S.wait_v = wait_v; S.sig_buf = tp ? sig_buf : -1; S.sig_v = sig_v; S.site = site; return S;
+    // layer stamps (tp.cuh): X carries stamp il when it enters layer il (0 = the embedding), il + 1 when layer il leaves it; FF / XD / XF of layer il carry il + 1
+    auto ts = [&](int in_buf, unsigned in_v, int add_buf, unsigned add_v, int out_buf, unsigned out_v) {
+        TpSync S;
+        if (tp) { S.in_buf = in_buf; S.in_v = in_v; S.add_buf = add_buf; S.add_v = add_v; S.out_buf = out_buf; S.out_v = out_v; }
+        return S;
     };
     int n = 0;
     auto pr = [&]() -> unsigned long long * { return P.prof && n < B200_PROF_SLOTS ? P.prof + n : nullptr; };   // timeline slot of the next launch
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
+    if (tp) { launch_k(tp_spread_kernel, dim3((e + 255) / 256), dim3(256), 0, st, (const float *)P.x, e, T); n++; }
     // attention: one cluster launch per layer (default) or the two-kernel variant (B200_ATTN_FUSED=0, or head sizes a cluster cannot cover)
     static const bool fused_env = !(getenv("B200_ATTN_FUSED") && getenv("B200_ATTN_FUSED")[0] == '0');
     const int nlay = (n_kv_bucket + 63) / 64 * 64;
@@ -582,7 +611,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
         const DecodeLayer &L = layers[il];
         const unsigned v = (unsigned)il + 1;                     // flag value of this layer's exchanges (tp.cuh)
         launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T,
-                 ts(il > 0 ? TPB_X : -1, (unsigned)il, -1, 0, 0)); n++;                 // x of layer il-1 (every rank's rows of w2 h + inpFF)
+                 ts(TPB_X, (unsigned)il, -1, 0, -1, 0)); n++;
         MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e_loc; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
         A.prof = pr(); launch_mmv<TYPE, EPI_QKV>(L.wqkv, A, st); n++;
@@ -597,7 +626,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
             B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
                                           (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, nlay, q81, off, s16, pr(),
-                                          T, ts(-1, 0, TPB_XD, v, il * 4 + 0), tp ? P.head0 : 0));
+                                          T, ts(-1, 0, -1, 0, TPB_XD, v), tp ? P.head0 : 0));
             n++;
         } else {
             launch_k(P.hd == 128 ? attn_kq_kernel<128> : attn_kq_kernel<64>, dim3((n_kv_bucket + 63) / 64, P.n_head), dim3(128), 0, st,
@@ -607,22 +636,25 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
                      P.n_head_kv, P.n_ctx, q81, off, s16, pr()); n++;
         }
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;
-        Bo.tp = T; Bo.ts = ts(TPB_XD, v, TPB_FF, v, il * 4 + 1); Bo.row0 = tp ? P.row0_e : 0; Bo.dst_buf = TPB_FF;
+        Bo.tp = T; Bo.ts = ts(TPB_XD, v, TPB_X, (unsigned)il, TPB_FF, v); Bo.row0 = tp ? P.row0_e : 0;
         Bo.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.wo, Bo, st); n++;
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T, ts(TPB_FF, v, -1, 0, 0)); n++;
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T, ts(TPB_FF, v, -1, 0, -1, 0)); n++;
         MmvArgs C{}; C.xpack = xpack_a; C.xpack_out = P.xpack_f; C.lut_silu = P.lut_silu; C.q81 = q81; C.off = off; C.scale16 = s16;
-        C.tp = T; C.ts = ts(-1, 0, TPB_XF, v, il * 4 + 2); C.row0 = tp ? P.row0_w13 : 0;
+        C.tp = T; C.ts = ts(-1, 0, -1, 0, TPB_XF, v); C.row0 = tp ? P.row0_w13 : 0;
         C.prof = pr(); launch_mmv<TYPE, EPI_SILU>(L.w13, C, st); n++;
         MmvArgs D{}; D.xpack = P.xpack_f; D.dst = P.x; D.addend = P.ff;
-        D.tp = T; D.ts = ts(TPB_XF, v, TPB_X, v, il * 4 + 3); D.row0 = tp ? P.row0_e : 0; D.dst_buf = TPB_X;
+        D.tp = T; D.ts = ts(TPB_XF, v, TPB_FF, v, TPB_X, v); D.row0 = tp ? P.row0_e : 0;
         D.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.w2, D, st); n++;
     }
     launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(), T,
-             ts(P.n_layer > 0 ? TPB_X : -1, (unsigned)P.n_layer, -1, 0, 0)); n++;
+             ts(TPB_X, (unsigned)P.n_layer, -1, 0, -1, 0)); n++;
     MmvArgs Z{}; Z.xpack = xpack_a; Z.dst = P.logits; Z.addend = nullptr; Z.n_past_inc = P.n_past;
-    Z.tp = T; Z.ts = ts(-1, 0, TPB_LOGITS, 1, P.n_layer * 4); Z.row0 = tp ? P.row0_v : 0; Z.dst_buf = TPB_LOGITS;
+    Z.tp = T; Z.ts = ts(-1, 0, -1, 0, TPB_LOGITS, 0); Z.row0 = tp ? P.row0_v : 0;
     Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS>(P.output, Z, st); n++;
-    if (tp) { launch_k(tp_fence_kernel, dim3(1), dim3(32), 0, st, T, ts(TPB_LOGITS, 1, -1, 0, 0)); n++; }
+    if (tp) {                                                    // gathered logits -> the plain array the host reads; then the epoch moves on
+        launch_k(tp_collect_kernel, dim3((P.n_vocab_full + 255) / 256), dim3(256), 0, st, P.logits, P.n_vocab_full, T); n++;
+        launch_k(tp_bump_kernel, dim3(1), dim3(32), 0, st, T); n++;
+    }
     B200_CHECK(cudaGetLastError());
     (void)f;
     if (launches) *launches = n;

@@ -552,25 +552,24 @@ static b200_session *start_session_tp(b200_session *s) {
     B200_CHECK(cudaMallocHost(&s->h_n_past, sizeof(int)));
     B200_CHECK(cudaMalloc(&s->d_prof, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
     B200_CHECK(cudaMemset(s->d_prof, 0, B200_PROF_SLOTS * 8 * sizeof(unsigned long long)));
-    // the exchange slab: x | ff | attention records | ffn records | logits | flags, 256-byte aligned pieces
+    // the exchange slab: arrays of 8-byte {word, tag} units (tp.cuh) -- x | ff | attention records | ffn records | logits, 256-byte aligned pieces
     TpCtx &T = s->dp.tp;
     T = TpCtx();
     T.world = G; T.rank = r; T.vmul = (unsigned)hp.n_layer + 1;
     size_t off = 0;
-    auto piece = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return (uint32_t)o; };
-    T.off[TPB_X] = piece(e * 4); T.off[TPB_FF] = piece(e * 4); T.off[TPB_XD] = piece((e / QK) * 64); T.off[TPB_XF] = piece((f / QK) * 64);
-    T.off[TPB_LOGITS] = piece(V * 4); T.off_flags = piece((size_t)TPB_COUNT * TP_MAX * 32);
+    auto piece = [&](size_t units) { const size_t o = off; off += (units * 8 + 255) & ~(size_t)255; return (uint32_t)o; };
+    T.off[TPB_X] = piece(e); T.off[TPB_FF] = piece(e); T.off[TPB_XD] = piece((e / QK) * 16); T.off[TPB_XF] = piece((f / QK) * 16); T.off[TPB_LOGITS] = piece(V);
     s->tp_slab_bytes = off;
     B200_CHECK(cudaMalloc(&s->tp_slab, off));
-    B200_CHECK(cudaMemset(s->tp_slab, 0, off));
-    B200_CHECK(cudaMalloc(&s->tp_state, (2 + (size_t)hp.n_layer * 4 + 1) * sizeof(unsigned)));
-    B200_CHECK(cudaMemset(s->tp_state, 0, (2 + (size_t)hp.n_layer * 4 + 1) * sizeof(unsigned)));
-    T.epoch = s->tp_state; T.arrivals = s->tp_state + 2;
+    B200_CHECK(cudaMemset(s->tp_slab, 0, off));                           // tag 0 never matches
+    B200_CHECK(cudaMalloc(&s->tp_state, 2 * sizeof(unsigned)));
+    B200_CHECK(cudaMemset(s->tp_state, 0, 2 * sizeof(unsigned)));
+    T.epoch = s->tp_state;
     for (int p = 0; p < TP_MAX; p++) T.peer[p] = nullptr;
     T.peer[r] = s->tp_slab;                                              // peers are mapped by b200_session_tp_connect
-    s->x = (float *)(s->tp_slab + T.off[TPB_X]); s->ff = (float *)(s->tp_slab + T.off[TPB_FF]);
-    s->xpack_d = (int4 *)(s->tp_slab + T.off[TPB_XD]); s->xpack_f = (int4 *)(s->tp_slab + T.off[TPB_XF]);
-    s->logits = (float *)(s->tp_slab + T.off[TPB_LOGITS]);
+    B200_CHECK(cudaMalloc(&s->x, e * 4));                                 // the embedding row (plain f32) before it is spread into the X units
+    B200_CHECK(cudaMalloc(&s->logits, V * 4));                            // the gathered logits, plain f32 for the host
+    s->ff = nullptr; s->xpack_d = nullptr; s->xpack_f = nullptr;
     const RopeTable &rt_ = rope_table(hp.n_rot, 0, hp.rope_freq_base, hp.rope_freq_scale, m->hd, (int)n_ctx);
     {
         std::vector<DecodeLayer> hl(hp.n_layer);
@@ -590,7 +589,7 @@ static b200_session *start_session_tp(b200_session *s) {
     P.token = s->d_tokens; P.n_past = s->d_n_past;
     P.x = s->x; P.q = s->qbuf; P.kq = nullptr; P.attn = nullptr; P.ff = s->ff; P.h13 = nullptr; P.logits = s->logits;
     P.xpack_d = s->xpack_d; P.xpack_f = s->xpack_f; P.bar = nullptr; P.scratch_bytes = 0;
-    P.e_loc = m->e_loc; P.head0 = r * (hp.n_head / G);
+    P.e_loc = m->e_loc; P.head0 = r * (hp.n_head / G); P.n_vocab_full = hp.n_vocab;
     P.row0_e = (int64_t)r * m->e_loc; P.row0_w13 = (int64_t)r * 2 * m->f_loc; P.row0_v = (int64_t)r * m->v_loc;
     P.prof = nullptr;
     QWeight probe; probe.nb = (int64_t)e / QK;
@@ -847,10 +846,9 @@ void b200_session_free(b200_session *s) {
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     if (s->h_n_past) B200_CHECK(cudaFreeHost(s->h_n_past));
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
-    if (s->tp_slab) {                                    // tensor-parallel session: x, ff, records and logits live inside the slab
+    if (s->tp_slab) {                                    // tensor-parallel session: the exchange slab and the peers' mappings
         for (int p = 0; p < TP_MAX; p++) if (s->tp_peer_map[p]) cudaIpcCloseMemHandle(s->tp_peer_map[p]);
         B200_CHECK(cudaFree(s->tp_slab)); B200_CHECK(cudaFree(s->tp_state));
-        s->x = s->ff = s->logits = nullptr; s->xpack_d = s->xpack_f = nullptr;
     }
     void *dev[] = {s->xpack_a, s->xpack_d, s->xpack_f, s->d_prof, s->d_layers, s->d_bar, s->d_n_past, s->qbuf, s->attn, s->tap, s->memory_k, s->memory_v, s->d_tokens, s->x, s->cur, s->ff, s->qkv, s->kq, s->h13, s->hmul, s->logits, s->xq, s->xds, s->xpack, s->xh, s->topk};
     for (void *p : dev) if (p) B200_CHECK(cudaFree(p));

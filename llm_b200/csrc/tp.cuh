@@ -8,10 +8,12 @@
 //   silu(w1 x) * (w3 x) (records)   -> w2's input        buffer XF
 //   w2 h + inpFF  (f32)             -> next rms_norm     buffer X
 //   logits (f32)                    -> the caller        buffer LOGITS
-// There is no collective call on the data path: the epilogue that produces a slice stores it straight into EVERY rank's buffer through peer-mapped
-// pointers (NVLink / NVSwitch P2P stores, CUDA IPC mappings of one "exchange slab" per rank), then the last CTA of the kernel releases a per-source flag
-// on every rank; the consuming kernel acquires the G flags before it reads the buffer.  Flags carry a monotonically increasing value
-// (epoch * (n_layer + 1) + layer + 1, epoch = tokens decoded so far) so nothing is ever reset.
+// There is no collective call and no fence on the data path.  Every 32-bit word travels as an 8-byte unit {payload, tag} written with ONE 64-bit store
+// straight into EVERY rank's buffer through peer-mapped pointers (NVLink / NVSwitch P2P stores, CUDA IPC mappings of one "exchange slab" per rank); an
+// aligned 8-byte store is single-copy atomic, so a consumer that polls a unit until its tag equals the expected one has the payload -- the low-latency
+// protocol NCCL calls LL.  tag = epoch * (n_layer + 1) + layer stamp + 1, epoch = tokens decoded so far: monotonic, nothing is ever reset, and a unit is
+// only rewritten after every rank consumed its previous content (the next write of a buffer needs results that depend on all ranks having read it).
+// Measured alternative (round 2, profiles/r02_notes.md): plain stores + __threadfence_system() + a per-kernel flag cost ~14 us per exchanging kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,66 +23,50 @@ namespace b200 {
 constexpr int TP_MAX = 8;
 enum { TPB_X = 0, TPB_FF = 1, TPB_XD = 2, TPB_XF = 3, TPB_LOGITS = 4, TPB_COUNT = 5 };
 
-struct TpCtx {                 // kernel argument (POD); world == 1: single GPU, every helper below degenerates to the local store
+struct TpCtx {                 // kernel argument (POD); world == 1: single GPU, the kernels use their plain local buffers
     int world = 1, rank = 0;
     char *peer[TP_MAX] = {};   // base of rank p's exchange slab as mapped in THIS process (peer[rank] is the local slab)
-    unsigned *epoch = nullptr;     // local: [0] tokens decoded so far, [1] number of flag waits that timed out (a peer died)
-    unsigned *arrivals = nullptr;  // local: one CTA-arrival counter per kernel site (5 per layer + 1)
-    uint32_t off[TPB_COUNT] = {};  // byte offsets of the buffers inside a slab
-    uint32_t off_flags = 0;        // [TPB_COUNT][TP_MAX] flags, 32 bytes apart
+    unsigned *epoch = nullptr;     // local: [0] tokens decoded so far, [1] number of polls that timed out (a peer died)
+    uint32_t off[TPB_COUNT] = {};  // byte offsets of the buffers (arrays of 8-byte units) inside a slab
     unsigned vmul = 1;             // n_layer + 1
-    int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): skip the flag waits -- results are garbage, the time is compute + stores only
+    int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): accept whatever a unit holds -- results are garbage, the time is compute + stores
 };
 
-// what one kernel instance waits for / signals (baked into the CUDA graph; the epoch is read from device memory)
+// what one kernel instance reads / writes (baked into the CUDA graph; the epoch is read from device memory)
 struct TpSync {
-    int wait_buf = -1; unsigned wait_v = 0;     // acquire flags[wait_buf][0..G) >= epoch * vmul + wait_v before reading the buffer
-    int sig_buf = -1; unsigned sig_v = 0;       // after the last CTA: flags[sig_buf][rank] = epoch * vmul + sig_v on every rank
-    int site = 0;                               // index into TpCtx::arrivals
-    int bump_epoch = 0;                         // the token's last kernel: epoch += 1 once every CTA has arrived
+    int in_buf = -1; unsigned in_v = 0;       // input vector / records come from this exchange buffer with layer stamp in_v (-1: local plain buffer)
+    int add_buf = -1; unsigned add_v = 0;     // residual addend (this rank's own slice of it)
+    int out_buf = -1; unsigned out_v = 0;     // results go to this buffer of every rank
 };
 
-__device__ __forceinline__ unsigned *tp_flag(const TpCtx &T, int p, int buf, int src) { return (unsigned *)(T.peer[p] + T.off_flags + (size_t)(buf * TP_MAX + src) * 32); }
+__device__ __forceinline__ unsigned tp_tag(const TpCtx &T, unsigned v) { return *(volatile unsigned *)T.epoch * T.vmul + v + 1u; }   // never 0 (the slab starts zeroed)
 
-__device__ __forceinline__ void tp_store_f32(const TpCtx &T, int buf, int64_t idx, float v) {
+__device__ __forceinline__ void tp_put(const TpCtx &T, int buf, int64_t unit, uint32_t payload, unsigned tag) {
 #pragma unroll 1
-    for (int p = 0; p < T.world; p++) ((float *)(T.peer[p] + T.off[buf]))[idx] = v;
-}
-__device__ __forceinline__ void tp_store_rec(const TpCtx &T, int buf, int64_t idx, int4 v) {
-#pragma unroll 1
-    for (int p = 0; p < T.world; p++) ((int4 *)(T.peer[p] + T.off[buf]))[idx] = v;
-}
-
-// one thread: spin until every rank's slice of `buf` for this (token, layer) has landed here
-__device__ __forceinline__ void tp_wait_thread(const TpCtx &T, const TpSync &S) {
-    if (T.world <= 1 || S.wait_buf < 0 || T.nowait) return;
-    const unsigned want = *(volatile unsigned *)T.epoch * T.vmul + S.wait_v;
-    for (int src = 0; src < T.world; src++) {
-        const unsigned *f = tp_flag(T, T.rank, S.wait_buf, src);
-        unsigned v;
-        const long long t0 = clock64();
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (clock64() - t0 > 6000000000LL) { atomicAdd(T.epoch + 1, 1u); break; }     // a peer is gone: do not hang the GPU, count it (b200_tp_timeouts)
-        } while ((int)(v - want) < 0);
+    for (int p = 0; p < T.world; p++) {
+        uint2 *dst = (uint2 *)(T.peer[p] + T.off[buf]) + unit;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(payload), "r"(tag) : "memory");
     }
 }
-
-// Called by ONE thread per CTA after every thread of the CTA has issued its remote stores and a CTA-level barrier (so the fence below orders them):
-// the last CTA to arrive publishes the flag on every rank.
-__device__ __forceinline__ void tp_signal_thread(const TpCtx &T, const TpSync &S, unsigned n_ctas) {
-    if (T.world <= 1 || S.sig_buf < 0) return;
-    const unsigned value = *(volatile unsigned *)T.epoch * T.vmul + S.sig_v;
-    __threadfence_system();
-    if (atomicAdd(T.arrivals + S.site, 1u) == n_ctas - 1) {
-        T.arrivals[S.site] = 0;
-        __threadfence_system();
-        for (int p = 0; p < T.world; p++) {
-            unsigned *f = tp_flag(T, p, S.sig_buf, T.rank);
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(value) : "memory");
-        }
-        if (S.bump_epoch) *T.epoch = *(volatile unsigned *)T.epoch + 1;
-    }
+__device__ __forceinline__ void tp_put_f32(const TpCtx &T, int buf, int64_t unit, float v, unsigned tag) { tp_put(T, buf, unit, __float_as_uint(v), tag); }
+__device__ __forceinline__ void tp_put_rec(const TpCtx &T, int buf, int64_t rec, int4 r, unsigned tag) {    // a 16-byte record = 4 units
+    tp_put(T, buf, rec * 4 + 0, (uint32_t)r.x, tag); tp_put(T, buf, rec * 4 + 1, (uint32_t)r.y, tag);
+    tp_put(T, buf, rec * 4 + 2, (uint32_t)r.z, tag); tp_put(T, buf, rec * 4 + 3, (uint32_t)r.w, tag);
 }
+
+// poll the LOCAL copy of a unit until its tag is the expected one
+__device__ __forceinline__ uint32_t tp_get(const TpCtx &T, int buf, int64_t unit, unsigned tag) {
+    const uint2 *src = (const uint2 *)(T.peer[T.rank] + T.off[buf]) + unit;
+    uint32_t v, t;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
+    if (t == tag || T.nowait) return v;
+    const long long t0 = clock64();
+    do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
+        if (clock64() - t0 > 6000000000LL) { atomicAdd(T.epoch + 1, 1u); break; }        // a peer is gone: do not hang the GPU, count it (b200_session_tp_timeouts)
+    } while (t != tag);
+    return v;
+}
+__device__ __forceinline__ float tp_get_f32(const TpCtx &T, int buf, int64_t unit, unsigned tag) { return __uint_as_float(tp_get(T, buf, unit, tag)); }
 
 }  // namespace b200

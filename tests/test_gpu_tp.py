@@ -71,15 +71,24 @@ def run_tp(tmp_path, world, cfg, quant, steps, port):
     env = dict(os.environ, OMP_NUM_THREADS="4", RESULT_DIR=str(tmp_path), TP_CFG=cfg, TP_QUANT=quant, TP_STEPS=str(steps))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=900, env=env)
-    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    if out.returncode != 0:                                        # keep the workers' own words (pytest truncates long assertion payloads)
+        dump = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(dump):
+            open(os.path.join(dump, f"tp_worker_w{world}_{quant}.stderr"), "w").write(out.stderr[-20000:])
+    assert out.returncode == 0, out.stderr[-1500:]
     return [json.loads((tmp_path / f"rank{i}.json").read_text()) for i in range(world)]
 
 
-@pytest.mark.parametrize("world,cfg,quant", [(2, "small", "q4_0"), (2, "small", "q5_1"), (4, "small", "q8_0")])
+# every K a multiple of 256 (the streaming mat-vec's granularity), whole heads and 32-row pieces per rank for 2 and 4 ranks; the second one is grouped-query
+TP_CFGS = {"mha": dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=8, n_layer=3, n_ff=1024, n_rot=64, n_ctx=256),
+           "gqa": dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=4, n_layer=2, n_ff=1024, n_rot=64, n_ctx=256)}
+
+
+@pytest.mark.parametrize("world,cfg,quant", [(2, "mha", "q4_0"), (2, "gqa", "q5_1"), (4, "mha", "q8_0")])
 def test_tensor_parallel_decode_bit_exact(tmp_path, world, cfg, quant):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    res = run_tp(tmp_path, world, cfg, quant, 40, 29530 + world)
+    res = run_tp(tmp_path, world, json.dumps(TP_CFGS[cfg]), quant, 40, 29530 + world)
     for r in res:
         assert r["bad"] == [] and r["kv_ok"] and r["timeouts"] == 0, r
 
