@@ -9,18 +9,17 @@
 // The eight S_L of a (token, row, block) are produced by the tensor core with a BLOCK-DIAGONAL B operand (same idea as exact_mma.cu, now in
 // tcgen05 form): for one half-block (16 elements = one kind::f16 K step)
 //     A = 128 tokens x 16 elements (the Q8 quants as f16, exact)            -- M = 128  = TMEM lanes
-//     B = (24 rows x 4 lanes) x 16 elements, column (n, l) non-zero only at elements 4l..4l+3 (the integer weights as f16, exact)   -- N = 96
+//     B = (32 rows x 4 lanes) x 16 elements, column (n, l) non-zero only at elements 4l..4l+3 (the integer weights as f16, exact)   -- N = 128
 //     D[t][(n, l)] = S_{4h+l}  exactly (|S| < 2^17; accumulate is OFF: every MMA is a fresh product)
-// Two MMAs (halves h = 0, 1) per block fill 192 TMEM columns = all eight partial dots of 128 tokens x 24 rows; TMEM holds two such blocks
-// so the tensor core runs one block ahead of the epilogue.  24 rows (not 32): an epilogue thread then owns 8 rows = 64 accumulators, which
-// lets THREE epilogue warps share each scheduler (register file: 12 x 32 x 152) -- the kernel is bound by how well the fp32 pipe is kept fed.  What stays on the CUDA cores is precisely the reference's rounding
+// Two MMAs (halves h = 0, 1) per block fill 256 TMEM columns = all eight partial dots of 128 tokens x 32 rows; TMEM holds two such blocks
+// (512 columns) so the tensor core runs one block ahead of the epilogue.  What stays on the CUDA cores is precisely the reference's rounding
 // sequence: one f32 product and eight ordered fmas per (token, row, block) = the bound of this kernel (fp32 pipe), see DESIGN.md section 4.
 //
-// Warp roles (512 threads):  warp 0   : TMA producer  -- cp.async.bulk.tensor of the f16 activations [128 tokens x 64 elements], 128B swizzle
+// Warp roles (384 threads):  warp 0   : TMA producer  -- cp.async.bulk.tensor of the f16 activations [128 tokens x 64 elements], 128B swizzle
 //                            warp 1   : MMA issuer    -- one thread: tcgen05.mma x 4 per stage, tcgen05.commit to the stage / TMEM barriers
 //                            warps 2-3: expanders     -- packed weights (L2) -> block-diagonal f16 B operands in shared memory + f32 scales
-//                            warps 4-15: epilogue     -- tcgen05.ld, the ordered fp32 chains (packed fma.rn.f32x2), final hsum, store
-// A thread of the epilogue IS a token (TMEM lane): it owns 8 rows x 8 lanes of accumulators; d_x is its private scalar, d_w is warp-uniform.
+//                            warps 4-11: epilogue     -- tcgen05.ld, the ordered fp32 chains (packed fma.rn.f32x2), final hsum, store
+// A thread of the epilogue IS a token (TMEM lane): it owns 16 rows x 8 lanes of accumulators; d_x is its private scalar, d_w is warp-uniform.
 #include <string.h>
 
 #include "kernels.cuh"
@@ -32,23 +31,19 @@ namespace {
 
 using namespace tc5;
 
-constexpr int TM = 128, TN = 24, NST = 4, DWR = 2 * NST + 4;     // tokens / rows per CTA, pipeline stages (2 blocks each), scale ring (blocks)
-constexpr int RPT = 8, NG = TN / RPT;                             // rows per epilogue thread, column groups (= epilogue warps per TMEM lane quarter)
-constexpr int HC = TN * 4, BUFC = 2 * HC;                         // TMEM columns of one half-block operand (96) / of one block (192)
-constexpr int WS = 32;                                            // floats per block in the scale ring planes (TN padded)
+constexpr int TM = 128, TN = 32, NST = 4, DWR = 2 * NST + 4;     // tokens / rows per CTA, pipeline stages (2 blocks each), scale ring (blocks)
 constexpr int A_STAGE = TM * 64 * 2;                              // 16 KB: [128 tokens][64 elements] f16, 128-byte rows, swizzled
 constexpr int B_LBO = 128, B_SBO = 272;                           // K-adjacent core matrices contiguous; 8-column groups 272 B apart (the expanders' 8-byte
                                                                   // stores then spread over the banks: 2-way instead of 8-way conflicts with 256)
-constexpr int B_HALF = (HC / 8) * B_SBO;                          // one block-diagonal operand (N = 96 columns x K = 16), no swizzle
+constexpr int B_HALF = 16 * B_SBO;                                // one block-diagonal operand (N = 128 columns x K = 16), no swizzle
 constexpr int B_STAGE = 4 * B_HALF;                               // [block j][half h]
 constexpr int XR = NST + 2, X_STAGE = TM * 16;                    // ring of per-stage activation scales: [token] float4 {d, aux} x 2 blocks
-constexpr int NEPI = 4 * NG;                                      // epilogue warps
-constexpr int NTHREADS = 128 + 32 * NEPI;                         // 4 producer-side warps + 12 epilogue warps = 512
-// setmaxnreg re-splits the CTA's OWN register pool (what the launch allocated: 512 threads x 128, the __launch_bounds__(512, 1) cap); a split that asks
+constexpr int NTHREADS = 384;
+// setmaxnreg re-splits the CTA's OWN register pool (what the launch allocated: 384 threads x 168, the __launch_bounds__(384, 1) cap); a split that asks
 // for more than the pool never completes (the kernel hangs in USETMAXREG.TRY_ALLOC)
-constexpr int PROD_REGS = 56, EPI_REGS = 152;
-static_assert(128 * PROD_REGS + 32 * NEPI * EPI_REGS <= NTHREADS * 128, "register split exceeds the CTA's pool");
-constexpr int SMEM_BYTES = 1024 + NST * (A_STAGE + B_STAGE) + 2 * DWR * WS * 4 + XR * X_STAGE + 256;
+constexpr int PROD_REGS = 56, EPI_REGS = 224;
+static_assert(128 * PROD_REGS + 256 * EPI_REGS <= NTHREADS * 168, "register split exceeds the CTA's pool");
+constexpr int SMEM_BYTES = 1024 + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + XR * X_STAGE + 256;
 
 template <int TYPE> struct Tc {
     static constexpr bool MIN = (TYPE == T_Q4_1 || TYPE == T_Q5_1), QH = (TYPE == T_Q5_0 || TYPE == T_Q5_1), Q8 = (TYPE == T_Q8_0);
@@ -75,12 +70,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;                     // 128B-swizzled tiles need 1024-byte alignment
     uint8_t *const sptr = smem_raw + (sbase - smem_u32(smem_raw));
-    constexpr int OFF_W = NST * (A_STAGE + B_STAGE), OFF_X = OFF_W + 2 * DWR * WS * 4, OFF_BAR = OFF_X + XR * X_STAGE;
-    const uint32_t sA = sbase, sB = sbase + NST * A_STAGE, sX = sbase + OFF_X, sBar = sbase + OFF_BAR;
+    const uint32_t sA = sbase, sB = sbase + NST * A_STAGE, sW = sB + NST * B_STAGE, sX = sW + DWR * TN * 8, sBar = sX + XR * X_STAGE;
     uint8_t *const pB = sptr + NST * A_STAGE;
-    float *const pWd = (float *)(sptr + OFF_W), *const pWm = pWd + DWR * WS;            // scale ring, two planes: d[DWR][WS] | m[DWR][WS]
-    const float4 *const pX = (const float4 *)(sptr + OFF_X);
-    uint32_t *const pTmem = (uint32_t *)(sptr + OFF_BAR + 128);
+    float2 *const pW = (float2 *)(sptr + NST * (A_STAGE + B_STAGE));
+    const float4 *const pX = (const float4 *)(sptr + NST * (A_STAGE + B_STAGE) + DWR * TN * 8);
+    uint32_t *const pTmem = (uint32_t *)(sptr + NST * (A_STAGE + B_STAGE) + DWR * TN * 8 + XR * X_STAGE + 128);
     auto bar_a_full = [&](int s) { return sBar + 8 * s; };
     auto bar_b_full = [&](int s) { return sBar + 8 * (NST + s); };
     auto bar_empty = [&](int s) { return sBar + 8 * (2 * NST + s); };
@@ -96,8 +90,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
     fence_proxy_async_smem();
     if (tid == 0) {
         tma_prefetch_desc(&tmap_x);
-        for (int s = 0; s < NST; s++) { mbar_init(bar_a_full(s), 1); mbar_init(bar_b_full(s), 2 * TN); mbar_init(bar_empty(s), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(bar_t_full(i), 1); mbar_init(bar_t_empty(i), NEPI); }
+        for (int s = 0; s < NST; s++) { mbar_init(bar_a_full(s), 1); mbar_init(bar_b_full(s), 64); mbar_init(bar_empty(s), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar_t_full(i), 1); mbar_init(bar_t_empty(i), 8); }
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(smem_u32(pTmem), 512); tmem_relinquish(); }
@@ -113,7 +107,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
             // ================= TMA producer =================
             if (lane == 0) {
                 const uint32_t x_bytes = (uint32_t)(B - m_base < TM ? B - m_base : TM) * 16u;
-                int xslot = 0;
                 for (int st = 0; st < nstage; st++) {
                     const int slot = st % NST; const uint32_t par = (st / NST) & 1;
                     mbar_wait(bar_empty(slot), par ^ 1, dead);
@@ -122,14 +115,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
                     // {d, aux} of this stage's two blocks for the tile's tokens: one contiguous piece of the block-pair-major scale array.  Ring of
                     // NST + 2 stages: slot st % XR is rewritten only after the MMAs of stage st - NST completed, i.e. after the epilogue has finished
                     // stage st - NST - 1 (the tensor core cannot run further ahead than the two TMEM buffers)
-                    bulk_load(sX + xslot * X_STAGE, xdt + ((size_t)st * B + m_base), x_bytes, bar_a_full(slot));
-                    if (++xslot == XR) xslot = 0;
+                    bulk_load(sX + (st % XR) * X_STAGE, xdt + ((size_t)st * B + m_base), x_bytes, bar_a_full(slot));
                 }
             }
         } else if (warp == 1) {
             // ================= MMA issuer =================
             if (lane == 0) {
-                constexpr uint32_t idesc = make_idesc_f16(128, HC);
+                constexpr uint32_t idesc = make_idesc_f16(128, 128);
                 for (int st = 0; st < nstage; st++) {
                     const int slot = st % NST; const uint32_t par = (st / NST) & 1;
                     mbar_wait(bar_a_full(slot), par, dead);
@@ -144,14 +136,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
                         for (int h = 0; h < 2; h++) {
                             const uint64_t ad = make_smem_desc(sA + slot * A_STAGE + j * 64 + h * 32, 16, 1024, LAYOUT_SW128);
                             const uint64_t bd = make_smem_desc(sB + slot * B_STAGE + (j * 2 + h) * B_HALF, B_LBO, B_SBO, LAYOUT_NONE);
-                            mma_f16_ss(tmem + buf * BUFC + h * HC, ad, bd, idesc, 0u);
+                            mma_f16_ss(tmem + buf * 256 + h * 128, ad, bd, idesc, 0u);
                         }
                         tc_commit(bar_t_full(buf));
                     }
                     tc_commit(bar_empty(slot));
                 }
             }
-        } else if (tid - 64 < 2 * TN) {
+        } else {
             // ================= expanders: thread (row r, half h) =================
             const int et = tid - 64, r = et >> 1, h = et & 1;
             const int64_t n = n_base + r < w.N ? n_base + r : w.N - 1;
@@ -165,7 +157,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
                 x.qh = T::QH ? h_ptr[blk] : 0u;
                 return x;
             };
-            // column (r, l) of half h: non-zero K slots 4l..4l+3  ->  8 bytes at this offset inside the operand
+            // column (r, l) of half h: non-zero K slots 4l..4l+3  ->  8 bytes at this offset inside the 4 KB operand
             uint32_t col_off[4];
 #pragma unroll
             for (int l = 0; l < 4; l++) col_off[l] = (uint32_t)((r >> 1) * B_SBO + (l >> 1) * B_LBO + (4 * (r & 1) + l) * 16 + (l & 1) * 8);
@@ -186,9 +178,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
                     f.y = bytes_to_half2(v, 0x4342u, T::OFF);
                     *(uint2 *)(out + col_off[l]) = f;
                 }
-                if (h == 0) {                                                                          // f32 scales of the row
-                    if (T::MIN) { __half2 hh; memcpy(&hh, &x.dm, 4); pWd[wslot * WS + r] = __low2float(hh); pWm[wslot * WS + r] = __high2float(hh); }
-                    else pWd[wslot * WS + r] = __half2float(__ushort_as_half((unsigned short)x.dm));
+                if (h == 0) {                                                                          // f32 scales, two planes: d[DWR][32] | m[DWR][32]
+                    float *pd = (float *)pW;
+                    if (T::MIN) { __half2 hh; memcpy(&hh, &x.dm, 4); pd[wslot * TN + r] = __low2float(hh); pd[DWR * TN + wslot * TN + r] = __high2float(hh); }
+                    else pd[wslot * TN + r] = __half2float(__ushort_as_half((unsigned short)x.dm));
                 }
             };
             WRaw c0[2], c1[2];                                                                     // two stages in flight
@@ -211,52 +204,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
             }
         }
     } else {
-        // ================= epilogue: thread = token (TMEM lane), 8 rows x 8 lanes; 3 warps per TMEM lane quarter = 3 per scheduler =================
-        // One chunk = the 8 rows x 4 lanes of ONE half-block = one 32-column tcgen05.ld.  Iteration: wait for the chunk's load (issued one iteration
-        // earlier), issue the next chunk's load, run this chunk's 16 packed fmas -- the TMEM latency hides behind the arithmetic of this warp and of
-        // the scheduler's two other epilogue warps.
+        // ================= epilogue: thread = token (TMEM lane), 16 rows x 8 lanes =================
+        // Software pipeline over "chunks" (4 rows = 2 x 16 TMEM columns): iteration g waits for the loads of chunk g (issued one iteration
+        // earlier), issues the loads of chunk g + 1 -- tcgen05.ld and the rows' weight scales -- and only then runs the fp32 chain of chunk g,
+        // so the TMEM / shared-memory latency hides behind 20 arithmetic instructions of the same warp (and the SM's other 7 epilogue warps).
         reg_alloc<EPI_REGS>();
-        const int q = warp & 3, g = (warp - 4) >> 2, tok = q * 32 + lane;
+        const int q = warp & 3, ch = (warp - 4) >> 2, tok = q * 32 + lane;
         const int64_t m = m_base + tok;
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + g * 32;
-        float2 acc[RPT][4];
-        float summs[RPT];
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + ch * 64;
+        float2 acc[16][4];
+        float summs[16];
 #pragma unroll
-        for (int r = 0; r < RPT; r++) { summs[r] = 0.f;
+        for (int r = 0; r < 16; r++) { summs[r] = 0.f;
 #pragma unroll
             for (int p = 0; p < 4; p++) acc[r][p] = make_float2(0.f, 0.f); }
 
+        // chunk = 8 rows x 4 lanes of ONE half-block = one 32-column tcgen05.ld (the wide loads use the TMEM read port best: profiles/r02_notes.md);
+        // order per block: (rows 0-7, lanes 0-3), (rows 0-7, lanes 4-7), (rows 8-15, lanes 0-3), (rows 8-15, lanes 4-7)
         uint32_t dA[32], dB[32];                                                                   // TMEM staging, double-buffered
-        float4 wd[2], wm[2];                                                                       // d (and m) of the thread's 8 rows for the block being computed
-        float sc[RPT];                                                                             // d_w * d_x (shared by the two halves)
-        int wslot = 0, xslot = 0;
-        auto issue = [&](int blk, int h, uint32_t (&d)[32]) {
+        float4 wd[2], wm[2];                                                                       // d (and m) of the chunk pair's 8 rows
+        float sc[8];                                                                               // d_w * d_x of those rows (shared by the two halves)
+        const float *pWd = (const float *)pW, *pWm = pWd + DWR * TN;                               // scale ring as two planes: d[DWR][32] | m[DWR][32]
+        int wslot = 0, xslot = 0;                                                                  // ring positions of the block / stage being LOADED next
+        auto issue = [&](int blk, int c, uint32_t (&d)[32]) {                                     // c = 0..3 as listed above
             const int buf = blk & 1;
-            if (h == 0) { mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead); tc_fence_after(); }
-            tmem_ld_x32(t_lane + buf * BUFC + h * HC, d);
+            if (c == 0) { mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead); tc_fence_after(); }
+            tmem_ld_x32(t_lane + buf * 256 + (c & 1) * 128 + (c >> 1) * 32, d);
         };
-        auto load_w = [&]() {                                                                      // the block in ring slot wslot; then advance
-            const float4 *pd = (const float4 *)(pWd + wslot * WS + g * RPT);
+        auto load_w = [&](int slot, int c2) {                                                     // rows 8 c2 .. 8 c2 + 7 of the block in ring slot `slot`
+            const float4 *pd = (const float4 *)(pWd + slot * TN + ch * 16 + c2 * 8);
             wd[0] = pd[0]; wd[1] = pd[1];
-            if (T::MIN) { const float4 *pm = (const float4 *)(pWm + wslot * WS + g * RPT); wm[0] = pm[0]; wm[1] = pm[1]; }
-            if (++wslot == DWR) wslot = 0;
+            if (T::MIN) { const float4 *pm = (const float4 *)(pWm + slot * TN + ch * 16 + c2 * 8); wm[0] = pm[0]; wm[1] = pm[1]; }
         };
-        auto compute = [&](int h, const uint32_t (&d)[32], float dx, float sx) {
+        auto compute = [&](int c, const uint32_t (&d)[32], float dx, float sx) {
+            const int h = c & 1, r0 = (c >> 1) * 8;
             if (h == 0) {
                 const float dws[8] = {wd[0].x, wd[0].y, wd[0].z, wd[0].w, wd[1].x, wd[1].y, wd[1].z, wd[1].w};
 #pragma unroll
-                for (int rr = 0; rr < RPT; rr++) sc[rr] = __fmul_rn(dws[rr], dx);
+                for (int rr = 0; rr < 8; rr++) sc[rr] = __fmul_rn(dws[rr], dx);
                 if (T::MIN) {
                     const float mws[8] = {wm[0].x, wm[0].y, wm[0].z, wm[0].w, wm[1].x, wm[1].y, wm[1].z, wm[1].w};
 #pragma unroll
-                    for (int rr = 0; rr < RPT; rr++) summs[rr] = __fmaf_rn(mws[rr], sx, summs[rr]);
+                    for (int rr = 0; rr < 8; rr++) summs[r0 + rr] = __fmaf_rn(mws[rr], sx, summs[r0 + rr]);
                 }
             }
 #pragma unroll
-            for (int rr = 0; rr < RPT; rr++) {
+            for (int rr = 0; rr < 8; rr++) {
                 const float2 s2 = make_float2(sc[rr], sc[rr]);
-                acc[rr][2 * h] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 0]), __uint_as_float(d[rr * 4 + 1])), acc[rr][2 * h]);
-                acc[rr][2 * h + 1] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 2]), __uint_as_float(d[rr * 4 + 3])), acc[rr][2 * h + 1]);
+                acc[r0 + rr][2 * h] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 0]), __uint_as_float(d[rr * 4 + 1])), acc[r0 + rr][2 * h]);
+                acc[r0 + rr][2 * h + 1] = ffma2(s2, make_float2(__uint_as_float(d[rr * 4 + 2]), __uint_as_float(d[rr * 4 + 3])), acc[r0 + rr][2 * h + 1]);
             }
         };
         auto release = [&](int blk) {                                                              // every column of the block's buffer is in registers
@@ -264,30 +260,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_t_empty(blk & 1));
         };
+        auto next_w = [&]() { int s0 = wslot; if (++wslot == DWR) wslot = 0; return s0; };
 
-        if (nstage > 0) { issue(0, 0, dA); load_w(); }
+        int ws = 0;                                                                                // ring slot of the block being computed
+        if (nstage > 0) { issue(0, 0, dA); ws = next_w(); load_w(ws, 0); }
         for (int st = 0; st < nstage; st++) {
-            const float4 xd = pX[xslot * TM + tok];                                                // the scales of this stage (landed with its activations)
+            // the scales of this stage (landed with the stage's activations, before its MMAs ran)
+            const float4 xd = pX[xslot * TM + tok];
             if (++xslot == XR) xslot = 0;
             const bool more = st + 1 < nstage;
             const int b0 = 2 * st, b1 = 2 * st + 1;
-            // the next block's weight scales are fetched after its tmem_full wait (the expander wrote them before the MMAs that barrier reports)
-            tc_wait_ld(); issue(b0, 1, dB); compute(0, dA, xd.x, xd.y);
-            tc_wait_ld(); release(b0); issue(b1, 0, dA); load_w(); compute(1, dB, xd.x, xd.y);
-            tc_wait_ld(); issue(b1, 1, dB); compute(0, dA, xd.z, xd.w);
-            tc_wait_ld(); release(b1); if (more) { issue(b1 + 1, 0, dA); load_w(); } compute(1, dB, xd.z, xd.w);
+            // the weight scales of rows 8-15 are fetched once compute(0) has turned rows 0-7's into sc[]; the next block's only after its tmem_full wait
+            // (the expander wrote them before the MMAs the barrier reports)
+            tc_wait_ld(); issue(b0, 1, dB); compute(0, dA, xd.x, xd.y); load_w(ws, 1);
+            tc_wait_ld(); issue(b0, 2, dA); compute(1, dB, xd.x, xd.y);
+            tc_wait_ld(); issue(b0, 3, dB); compute(2, dA, xd.x, xd.y);
+            tc_wait_ld(); release(b0); issue(b1, 0, dA); ws = next_w(); load_w(ws, 0); compute(3, dB, xd.x, xd.y);
+            tc_wait_ld(); issue(b1, 1, dB); compute(0, dA, xd.z, xd.w); load_w(ws, 1);
+            tc_wait_ld(); issue(b1, 2, dA); compute(1, dB, xd.z, xd.w);
+            tc_wait_ld(); issue(b1, 3, dB); compute(2, dA, xd.z, xd.w);
+            tc_wait_ld(); release(b1); if (more) { issue(b1 + 1, 0, dA); ws = next_w(); load_w(ws, 0); } compute(3, dB, xd.z, xd.w);
         }
         // hsum_float_8 (LC/ggml.c:608-616): ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), then + summs
         if (m < B) {
-            float *out = dst + (size_t)m * ldd + n_base + g * RPT;
-            const float *add = addend ? addend + (size_t)m * lda + n_base + g * RPT : nullptr;
+            float *out = dst + (size_t)m * ldd + n_base + ch * 16;
+            const float *add = addend ? addend + (size_t)m * lda + n_base + ch * 16 : nullptr;
 #pragma unroll
-            for (int r = 0; r < RPT; r++) {
+            for (int r = 0; r < 16; r++) {
                 const float a0 = acc[r][0].x, a1 = acc[r][0].y, a2 = acc[r][1].x, a3 = acc[r][1].y;
                 const float a4 = acc[r][2].x, a5 = acc[r][2].y, a6 = acc[r][3].x, a7 = acc[r][3].y;
                 float v = __fadd_rn(__fadd_rn(__fadd_rn(a0, a4), __fadd_rn(a2, a6)), __fadd_rn(__fadd_rn(a1, a5), __fadd_rn(a3, a7)));
                 if (T::MIN) v = __fadd_rn(v, summs[r]);
-                if (n_base + g * RPT + r < w.N) out[r] = add ? __fadd_rn(v, add[r]) : v;
+                if (n_base + ch * 16 + r < w.N) out[r] = add ? __fadd_rn(v, add[r]) : v;
             }
         }
     }
