@@ -27,6 +27,10 @@ namespace b200 {
 
 using namespace stream;
 
+// the tensor-parallel context of this process's session (tp.cuh): one copy in constant memory instead of ~120 bytes in every kernel's argument block
+// (the single-GPU decode graph must not pay for it: 227 launches per token).  world == 0 / 1: single GPU.
+__constant__ TpCtx c_tp;
+
 namespace {
 
 // Programmatic dependent launch.  Every kernel of the chain touches nothing a predecessor writes (and writes nothing at all) before
@@ -74,7 +78,8 @@ __device__ __forceinline__ float f16dot_tree(float s) {          // ggml_vec_dot
 // ---- 1 / 6: rms_norm * gain -> records.  grid = e/128 CTAs of 256 threads; every CTA reduces the whole row (16 KB from L2) and
 //      quantizes its own 4 blocks per warp pass. ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
-                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpCtx T, const TpSync S) {
+                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpSync S) {
+    const TpCtx &T = c_tp;
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
@@ -138,7 +143,7 @@ struct MmvArgs {
     // EPI_BIAS: dst = ((W x + bias) [+ add1]) [+ add2] in that order (ggml_add nodes of gptneox lib.rs:200,302,308-325); EPI_GELU: gelu(W x + bias) quantized
     const float *bias, *add1, *add2; const uint16_t *lut_gelu;
     // tensor-parallel decode (tp.cuh): this rank owns rows [row0, row0 + w.N) of the full matrix; results go to buffer dst_buf of every rank
-    TpCtx tp; TpSync ts; int64_t row0;
+    TpSync ts; int64_t row0;
 };
 
 template <int TYPE, int EPI>
@@ -159,9 +164,9 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         return;
     }
     pdl_wait();
-    if (A.tp.world > 1 && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
-        const unsigned tag = tp_tag(A.tp, A.ts.in_v);
-        for (int i = tid; i < (int)w.nb * 16; i += SCOMPUTE) ((uint32_t *)sx)[i] = tp_get(A.tp, A.ts.in_buf, i, tag);
+    if (c_tp.world > 1 && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
+        const unsigned tag = tp_tag(c_tp, A.ts.in_v);
+        for (int i = tid; i < (int)w.nb * 16; i += SCOMPUTE) ((uint32_t *)sx)[i] = tp_get(c_tp, A.ts.in_buf, i, tag);
     } else {
         for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -174,9 +179,9 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
             if ((tid & 3) != 0 || row >= w.N) return;
             const int64_t g = A.row0 + row;                      // row of the full matrix (row0 = 0 on a single GPU)
-            if (A.tp.world > 1) {                                // addend: this rank's own slice of the gathered vector; result: to every rank
-                const float out = A.ts.add_buf >= 0 ? __fadd_rn(v, tp_get_f32(A.tp, A.ts.add_buf, g, tp_tag(A.tp, A.ts.add_v))) : v;
-                tp_put_f32(A.tp, A.ts.out_buf, g, out, tp_tag(A.tp, A.ts.out_v));
+            if (c_tp.world > 1) {                                // addend: this rank's own slice of the gathered vector; result: to every rank
+                const float out = A.ts.add_buf >= 0 ? __fadd_rn(v, tp_get_f32(c_tp, A.ts.add_buf, g, tp_tag(c_tp, A.ts.add_v))) : v;
+                tp_put_f32(c_tp, A.ts.out_buf, g, out, tp_tag(c_tp, A.ts.out_v));
             } else A.dst[g] = A.addend ? __fadd_rn(v, __ldcg(A.addend + g)) : v;
         }, 1, A.prof);
         if (EPI == EPI_LOGITS && blockIdx.x == 0 && tid == 0) *A.n_past_inc = *A.n_past_inc + 1;
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
                 const int64_t blk = (A.row0 >> 6) + (row >> 6);     // block of w2's input (row0 counts this rank's interleaved w1|w3 rows)
                 int4 rec;
                 if (pack_quad_rec(hm, lane, lane < 8, A.q81, A.off, A.scale16, rec)) {
-                    if (A.tp.world > 1) tp_put_rec(A.tp, TPB_XF, blk * 4 + (lane & 7), rec, tp_tag(A.tp, A.ts.out_v)); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
+                    if (c_tp.world > 1) tp_put_rec(c_tp, TPB_XF, blk * 4 + (lane & 7), rec, tp_tag(c_tp, A.ts.out_v)); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
                 }
             }
             compute_sync();
@@ -402,7 +407,8 @@ constexpr int ATH = 256;
 __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, const __half *__restrict__ Vl,
                                                          int4 *__restrict__ xpack_out, const int *__restrict__ n_past, const uint16_t *__restrict__ lut_exp,
                                                          float kq_scale, int hd, int n_head, int n_head_kv, int gqa, int n_ctx, int nlay, int q81, int off, int scale16,
-                                                         unsigned long long *prof, const TpCtx T, const TpSync S, int head0) {
+                                                         unsigned long long *prof, const TpSync S, int head0) {
+    const TpCtx &T = c_tp;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) uint8_t sm[];
@@ -562,19 +568,22 @@ void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
 
 // tensor-parallel helpers (tp.cuh).  spread: the embedding row every rank computed for itself -> the X exchange buffer's unit form (stamp 0);
 // collect: the gathered logits units -> the plain f32 logits array the host reads; bump: the token is complete, the epoch moves on.
-__global__ void __launch_bounds__(256) tp_spread_kernel(const float *__restrict__ x, int n, const TpCtx T) {
+__global__ void __launch_bounds__(256) tp_spread_kernel(const float *__restrict__ x, int n) {
+    const TpCtx &T = c_tp;
     pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     uint2 *dst = (uint2 *)(T.peer[T.rank] + T.off[TPB_X]) + i;
     *dst = make_uint2(__float_as_uint(__ldcg(x + i)), tp_tag(T, 0));
 }
-__global__ void __launch_bounds__(256) tp_collect_kernel(float *__restrict__ logits, int n, const TpCtx T) {
+__global__ void __launch_bounds__(256) tp_collect_kernel(float *__restrict__ logits, int n) {
+    const TpCtx &T = c_tp;
     pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < n) logits[i] = tp_get_f32(T, TPB_LOGITS, i, tp_tag(T, 0));
 }
-__global__ void tp_bump_kernel(const TpCtx T) {
+__global__ void tp_bump_kernel() {
+    const TpCtx &T = c_tp;
     pdl_wait();
     if (threadIdx.x == 0) *T.epoch = *(volatile unsigned *)T.epoch + 1;
 }
@@ -595,7 +604,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     int n = 0;
     auto pr = [&]() -> unsigned long long * { return P.prof && n < B200_PROF_SLOTS ? P.prof + n : nullptr; };   // timeline slot of the next launch
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
-    if (tp) { launch_k(tp_spread_kernel, dim3((e + 255) / 256), dim3(256), 0, st, (const float *)P.x, e, T); n++; }
+    if (tp) { launch_k(tp_spread_kernel, dim3((e + 255) / 256), dim3(256), 0, st, (const float *)P.x, e); n++; }
     // attention: one cluster launch per layer (default) or the two-kernel variant (B200_ATTN_FUSED=0, or head sizes a cluster cannot cover)
     static const bool fused_env = !(getenv("B200_ATTN_FUSED") && getenv("B200_ATTN_FUSED")[0] == '0');
     const int nlay = (n_kv_bucket + 63) / 64 * 64;
@@ -610,7 +619,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     for (int il = 0; il < P.n_layer; il++) {
         const DecodeLayer &L = layers[il];
         const unsigned v = (unsigned)il + 1;                     // flag value of this layer's exchanges (tp.cuh)
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T,
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(),
                  ts(TPB_X, (unsigned)il, -1, 0, -1, 0)); n++;
         MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e_loc; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
@@ -626,7 +635,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
             B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
                                           (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, nlay, q81, off, s16, pr(),
-                                          T, ts(-1, 0, -1, 0, TPB_XD, v), tp ? P.head0 : 0));
+                                          ts(-1, 0, -1, 0, TPB_XD, v), tp ? P.head0 : 0));
             n++;
         } else {
             launch_k(P.hd == 128 ? attn_kq_kernel<128> : attn_kq_kernel<64>, dim3((n_kv_bucket + 63) / 64, P.n_head), dim3(128), 0, st,
@@ -636,24 +645,24 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
                      P.n_head_kv, P.n_ctx, q81, off, s16, pr()); n++;
         }
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;
-        Bo.tp = T; Bo.ts = ts(TPB_XD, v, TPB_X, (unsigned)il, TPB_FF, v); Bo.row0 = tp ? P.row0_e : 0;
+        Bo.ts = ts(TPB_XD, v, TPB_X, (unsigned)il, TPB_FF, v); Bo.row0 = tp ? P.row0_e : 0;
         Bo.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.wo, Bo, st); n++;
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), T, ts(TPB_FF, v, -1, 0, -1, 0)); n++;
+        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), ts(TPB_FF, v, -1, 0, -1, 0)); n++;
         MmvArgs C{}; C.xpack = xpack_a; C.xpack_out = P.xpack_f; C.lut_silu = P.lut_silu; C.q81 = q81; C.off = off; C.scale16 = s16;
-        C.tp = T; C.ts = ts(-1, 0, -1, 0, TPB_XF, v); C.row0 = tp ? P.row0_w13 : 0;
+        C.ts = ts(-1, 0, -1, 0, TPB_XF, v); C.row0 = tp ? P.row0_w13 : 0;
         C.prof = pr(); launch_mmv<TYPE, EPI_SILU>(L.w13, C, st); n++;
         MmvArgs D{}; D.xpack = P.xpack_f; D.dst = P.x; D.addend = P.ff;
-        D.tp = T; D.ts = ts(TPB_XF, v, TPB_FF, v, TPB_X, v); D.row0 = tp ? P.row0_e : 0;
+        D.ts = ts(TPB_XF, v, TPB_FF, v, TPB_X, v); D.row0 = tp ? P.row0_e : 0;
         D.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.w2, D, st); n++;
     }
-    launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(), T,
+    launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(),
              ts(TPB_X, (unsigned)P.n_layer, -1, 0, -1, 0)); n++;
     MmvArgs Z{}; Z.xpack = xpack_a; Z.dst = P.logits; Z.addend = nullptr; Z.n_past_inc = P.n_past;
-    Z.tp = T; Z.ts = ts(-1, 0, -1, 0, TPB_LOGITS, 0); Z.row0 = tp ? P.row0_v : 0;
+    Z.ts = ts(-1, 0, -1, 0, TPB_LOGITS, 0); Z.row0 = tp ? P.row0_v : 0;
     Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS>(P.output, Z, st); n++;
     if (tp) {                                                    // gathered logits -> the plain array the host reads; then the epoch moves on
-        launch_k(tp_collect_kernel, dim3((P.n_vocab_full + 255) / 256), dim3(256), 0, st, P.logits, P.n_vocab_full, T); n++;
-        launch_k(tp_bump_kernel, dim3(1), dim3(32), 0, st, T); n++;
+        launch_k(tp_collect_kernel, dim3((P.n_vocab_full + 255) / 256), dim3(256), 0, st, P.logits, P.n_vocab_full); n++;
+        launch_k(tp_bump_kernel, dim3(1), dim3(32), 0, st); n++;
     }
     B200_CHECK(cudaGetLastError());
     (void)f;
@@ -756,7 +765,7 @@ void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n
     static size_t fa_set = 48 * 1024;
     if (fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
     const dim3 ln_grid((e / 4 + 255) / 256);
-    const TpCtx T{}; const TpSync S{};
+    const TpSync S{};
     for (int il = 0; il < P.n_layer; il++) {
         const NeoxLayer &L = layers[il];
         launch_k(ln_pack_kernel, ln_grid, dim3(256), 0, st, (const float *)P.x, L.ln1_g, L.ln1_b, P.xpack_a, e, q81, off, s16); n++;          // :192-196
@@ -775,7 +784,7 @@ void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
             B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
                                           (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head, e, P.n_ctx, nlay, q81, off, s16,
-                                          (unsigned long long *)nullptr, T, S, 0));                                                           // :250-298
+                                          (unsigned long long *)nullptr, S, 0));                                                           // :250-298
             n++;
         }
         // attention.dense (+bias); sequential residual: ff_in = that + inpL                                                                    :301-312
@@ -807,6 +816,13 @@ void neox_decode_enqueue(const NeoxParams &P, const std::vector<NeoxLayer> &laye
         case T_Q8_0: neox_ops_t<T_Q8_0>(P, layers, n_kv_bucket, st, launches); break;
         default: B200_ASSERT(!"neox_decode_enqueue: unsupported weight type");
     }
+}
+
+// the process's tensor-parallel context (session.cu calls it after the slabs are connected and when the measurement switch flips); not inside a stream capture
+void decode_set_tp(const TpCtx &T, cudaStream_t st) {
+    B200_CHECK(cudaStreamSynchronize(st));
+    B200_CHECK(cudaMemcpyToSymbol(c_tp, &T, sizeof(TpCtx)));
+    B200_CHECK(cudaDeviceSynchronize());
 }
 
 // Enqueue one decode step (position read from *P.n_past on the device) on `st`.  n_kv_bucket >= n_past + 1 sizes the KQ grid.

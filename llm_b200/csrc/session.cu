@@ -823,12 +823,14 @@ int b200_session_tp_connect(b200_session *s, const void *handles_by_rank) {
         T.peer[p] = (char *)ptr;
     }
     s->tp_connected = true;
+    decode_set_tp(T, rt().stream);
     return B200_OK;
 }
 int b200_session_tp_set_nowait(b200_session *s, int32_t nowait) {     // measurement aid: the captured graphs carry the flag, so they are dropped
     if (!s || !s->tp_slab) return B200_ERR_BAD_ARG;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
     s->dp.tp.nowait = nowait ? 1 : 0;
+    decode_set_tp(s->dp.tp, rt().stream);
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
     s->graphs.clear();
     return B200_OK;
