@@ -86,13 +86,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     pdl_wait();
     const bool tp = T.world > 1;                               // tensor-parallel: the row is an array of {value, tag} units filled by every rank (tp.cuh)
     const unsigned tag = tp ? tp_tag(T, S.in_v) : 0u;
-    auto ld4 = [&](int i) {
-        if (!tp) return __ldcg((const float4 *)x + i);
-        float4 v;
-        v.x = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 0, tag); v.y = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 1, tag);
-        v.z = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 2, tag); v.w = tp_get_f32(T, S.in_buf, 4 * (int64_t)i + 3, tag);
-        return v;
-    };
+
     prof_begin(prof);
     // this CTA's 32 blocks are float4s [blockIdx.x * 256, +256) of the row: thread tid packs float4 blockIdx.x * 256 + tid, which is also
     // one of the values it sums -- the row is read once, all loads (row and gains) are in flight before the first use (one L2 round trip)
@@ -104,8 +98,22 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     constexpr int U = 4;
     for (int i0 = tid; i0 < nv; i0 += 256 * U) {
         float4 v[U];
+        if (!tp) {
 #pragma unroll
-        for (int k = 0; k < U; k++) { const int i = i0 + 256 * k; v[k] = i < nv ? ld4(i) : make_float4(0.f, 0.f, 0.f, 0.f); }   // written by a predecessor: L2-coherent load
+            for (int k = 0; k < U; k++) { const int i = i0 + 256 * k; v[k] = i < nv ? __ldcg((const float4 *)x + i) : make_float4(0.f, 0.f, 0.f, 0.f); }   // written by a predecessor: L2-coherent load
+        } else {                                                // float4 i = units 4i .. 4i+3 = pairs 2i, 2i+1: all loads first, then the tag checks
+            uint4 ra[U], rb[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) { const int i = i0 + 256 * k; if (i < nv) { ra[k] = tp_ld2(T, S.in_buf, 2 * (int64_t)i); rb[k] = tp_ld2(T, S.in_buf, 2 * (int64_t)i + 1); } }
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                const int i = i0 + 256 * k;
+                if (i < nv) {
+                    tp_fix2(T, S.in_buf, 2 * (int64_t)i, tag, ra[k]); tp_fix2(T, S.in_buf, 2 * (int64_t)i + 1, tag, rb[k]);
+                    v[k] = make_float4(__uint_as_float(ra[k].x), __uint_as_float(ra[k].z), __uint_as_float(rb[k].x), __uint_as_float(rb[k].z));
+                } else v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < U; k++) {
             if (i0 + 256 * k == mine) xv = v[k];
@@ -166,7 +174,18 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
     pdl_wait();
     if (c_tp.world > 1 && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
         const unsigned tag = tp_tag(c_tp, A.ts.in_v);
-        for (int i = tid; i < (int)w.nb * 16; i += SCOMPUTE) ((uint32_t *)sx)[i] = tp_get(c_tp, A.ts.in_buf, i, tag);
+        const int npair = (int)w.nb * 8;                        // a 16-byte record = 4 units = 2 pairs
+        constexpr int U = 8;                                    // 16-byte loads in flight per thread
+        for (int i0 = tid; i0 < npair; i0 += SCOMPUTE * U) {
+            uint4 v[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) { const int i = i0 + k * SCOMPUTE; if (i < npair) v[k] = tp_ld2(c_tp, A.ts.in_buf, i); }
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                const int i = i0 + k * SCOMPUTE;
+                if (i < npair) { tp_fix2(c_tp, A.ts.in_buf, i, tag, v[k]); ((uint2 *)sx)[i] = make_uint2(v[k].x, v[k].z); }
+            }
+        }
     } else {
         for (int i = tid; i < (int)w.nb * 4; i += SCOMPUTE) cp16(smem_u32(sx + i), A.xpack + i);   // all 16-byte copies in flight at once
         asm volatile("cp.async.wait_all;" ::: "memory");

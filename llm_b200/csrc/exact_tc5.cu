@@ -226,9 +226,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
         float sc[8];                                                                               // d_w * d_x of those rows (shared by the two halves)
         const float *pWd = (const float *)pW, *pWm = pWd + DWR * TN;                               // scale ring as two planes: d[DWR][32] | m[DWR][32]
         int wslot = 0, xslot = 0;                                                                  // ring positions of the block / stage being LOADED next
+        // The barrier probe of a block's first load is hoisted one chunk ahead of its use (`probe`): an mbarrier try_wait takes ~100 cycles to answer even when
+        // the phase is already complete, and issued early it answers behind the fp32 chain of the previous chunk instead of in front of the TMEM load.
+        bool rdy = false;
+        auto probe = [&](int blk) { rdy = dead || mbar_try_wait(bar_t_full(blk & 1), (blk >> 1) & 1); };
         auto issue = [&](int blk, int c, uint32_t (&d)[32]) {                                     // c = 0..3 as listed above
             const int buf = blk & 1;
-            if (c == 0) { mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead); tc_fence_after(); }
+            if (c == 0) { if (!rdy) mbar_wait(bar_t_full(buf), (blk >> 1) & 1, dead); tc_fence_after(); }
             tmem_ld_x32(t_lane + buf * 256 + (c & 1) * 128 + (c >> 1) * 32, d);
         };
         auto load_w = [&](int slot, int c2) {                                                     // rows 8 c2 .. 8 c2 + 7 of the block in ring slot `slot`
@@ -274,11 +278,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mm_exact_tc5_kernel(const __grid_
             // (the expander wrote them before the MMAs the barrier reports)
             tc_wait_ld(); issue(b0, 1, dB); compute(0, dA, xd.x, xd.y); load_w(ws, 1);
             tc_wait_ld(); issue(b0, 2, dA); compute(1, dB, xd.x, xd.y);
-            tc_wait_ld(); issue(b0, 3, dB); compute(2, dA, xd.x, xd.y);
+            tc_wait_ld(); issue(b0, 3, dB); probe(b1); compute(2, dA, xd.x, xd.y);
             tc_wait_ld(); release(b0); issue(b1, 0, dA); ws = next_w(); load_w(ws, 0); compute(3, dB, xd.x, xd.y);
             tc_wait_ld(); issue(b1, 1, dB); compute(0, dA, xd.z, xd.w); load_w(ws, 1);
             tc_wait_ld(); issue(b1, 2, dA); compute(1, dB, xd.z, xd.w);
-            tc_wait_ld(); issue(b1, 3, dB); compute(2, dA, xd.z, xd.w);
+            tc_wait_ld(); issue(b1, 3, dB); if (more) probe(b1 + 1); compute(2, dA, xd.z, xd.w);
             tc_wait_ld(); release(b1); if (more) { issue(b1 + 1, 0, dA); ws = next_w(); load_w(ws, 0); } compute(3, dB, xd.z, xd.w);
         }
         // hsum_float_8 (LC/ggml.c:608-616): ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), then + summs

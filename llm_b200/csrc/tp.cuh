@@ -67,6 +67,18 @@ __device__ __forceinline__ uint32_t tp_get(const TpCtx &T, int buf, int64_t unit
     } while (t != tag);
     return v;
 }
+// Two units per 16-byte load, for consumers that read many units: issue ALL the loads first (tp_ld2), then check the tags (tp_fix2) -- the polling branch
+// of tp_get serialises a thread's loads at one L2 round trip each (measured: 6.8 us to gather w2's input records that way, profiles/r02_notes.md).
+__device__ __forceinline__ uint4 tp_ld2(const TpCtx &T, int buf, int64_t pair) {
+    const uint4 *src = (const uint4 *)(T.peer[T.rank] + T.off[buf]) + pair;
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tp_fix2(const TpCtx &T, int buf, int64_t pair, unsigned tag, uint4 &v) {     // payloads end up in v.x and v.z
+    if (v.y != tag) v.x = tp_get(T, buf, 2 * pair, tag);
+    if (v.w != tag) v.z = tp_get(T, buf, 2 * pair + 1, tag);
+}
 __device__ __forceinline__ float tp_get_f32(const TpCtx &T, int buf, int64_t unit, unsigned tag) { return __uint_as_float(tp_get(T, buf, unit, tag)); }
 
 }  // namespace b200
