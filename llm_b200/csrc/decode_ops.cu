@@ -77,6 +77,7 @@ __device__ __forceinline__ float f16dot_tree(float s) {          // ggml_vec_dot
 
 // ---- 1 / 6: rms_norm * gain -> records.  grid = e/128 CTAs of 256 threads; every CTA reduces the whole row (16 KB from L2) and
 //      quantizes its own 4 blocks per warp pass. ------------------------------------------------------------------------------------
+template <bool TP>
 __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
                                                         int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpSync S) {
     const TpCtx &T = c_tp;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
     pdl_wait();
-    const bool tp = T.world > 1;                               // tensor-parallel: the row is an array of {value, tag} units filled by every rank (tp.cuh)
+    constexpr bool tp = TP;                                    // tensor-parallel: the row is an array of {value, tag} units filled by every rank (tp.cuh)
     const unsigned tag = tp ? tp_tag(T, S.in_v) : 0u;
 
     prof_begin(prof);
@@ -154,7 +155,7 @@ struct MmvArgs {
     TpSync ts; int64_t row0;
 };
 
-template <int TYPE, int EPI>
+template <int TYPE, int EPI, bool TP>
 __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, const MmvArgs A) {
     const bool pdl_early = A.pdl_early != 0;
     using T = St<TYPE>;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         return;
     }
     pdl_wait();
-    if (c_tp.world > 1 && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
+    if (TP && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
         const unsigned tag = tp_tag(c_tp, A.ts.in_v);
         const int npair = (int)w.nb * 8;                        // a 16-byte record = 4 units = 2 pairs
         constexpr int U = 8;                                    // 16-byte loads in flight per thread
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         consume_matvec<TYPE>(w, sx, R, blockIdx.x, gridDim.x, tid, [&](int64_t row, float v) {
             if ((tid & 3) != 0 || row >= w.N) return;
             const int64_t g = A.row0 + row;                      // row of the full matrix (row0 = 0 on a single GPU)
-            if (c_tp.world > 1) {                                // addend: this rank's own slice of the gathered vector; result: to every rank
+            if (TP) {                                            // addend: this rank's own slice of the gathered vector; result: to every rank
                 const float out = A.ts.add_buf >= 0 ? __fadd_rn(v, tp_get_f32(c_tp, A.ts.add_buf, g, tp_tag(c_tp, A.ts.add_v))) : v;
                 tp_put_f32(c_tp, A.ts.out_buf, g, out, tp_tag(c_tp, A.ts.out_v));
             } else A.dst[g] = A.addend ? __fadd_rn(v, __ldcg(A.addend + g)) : v;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
                 const int64_t blk = (A.row0 >> 6) + (row >> 6);     // block of w2's input (row0 counts this rank's interleaved w1|w3 rows)
                 int4 rec;
                 if (pack_quad_rec(hm, lane, lane < 8, A.q81, A.off, A.scale16, rec)) {
-                    if (c_tp.world > 1) tp_put_rec(c_tp, TPB_XF, blk * 4 + (lane & 7), rec, tp_tag(c_tp, A.ts.out_v)); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
+                    if (TP) tp_put_rec(c_tp, TPB_XF, blk * 4 + (lane & 7), rec, tp_tag(c_tp, A.ts.out_v)); else A.xpack_out[blk * 4 + (lane & 7)] = rec;
                 }
             }
             compute_sync();
@@ -423,6 +424,7 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const int4 &a, const int4 
 }
 
 constexpr int ATH = 256;
+template <bool TP>
 __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict__ q, const __half *__restrict__ Kl, const __half *__restrict__ Vl,
                                                          int4 *__restrict__ xpack_out, const int *__restrict__ n_past, const uint16_t *__restrict__ lut_exp,
                                                          float kq_scale, int hd, int n_head, int n_head_kv, int gqa, int n_ctx, int nlay, int q81, int off, int scale16,
@@ -540,13 +542,13 @@ __global__ void __launch_bounds__(ATH) attn_fused_kernel(const float *__restrict
         int4 rec;
         const int64_t blk = (int64_t)(((head0 + h) * hd + c0) / QK);       // block of wo's input: heads are global (head0 = first head of this rank)
         if (pack_quad_rec(((const float4 *)stash)[lane & 7], lane, lane < 8, q81, off, scale16, rec)) {
-            if (T.world > 1) tp_put_rec(T, TPB_XD, blk * 4 + (lane & 7), rec, tp_tag(T, S.out_v)); else xpack_out[blk * 4 + (lane & 7)] = rec;
+            if (TP) tp_put_rec(T, TPB_XD, blk * 4 + (lane & 7), rec, tp_tag(T, S.out_v)); else xpack_out[blk * 4 + (lane & 7)] = rec;
         }
     }
     prof_end(prof);
 }
 
-template <int TYPE, int EPI>
+template <int TYPE, int EPI, bool TP = false>
 void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
     constexpr int ROWS = SR, CB = SCB;
     using T = St<TYPE>;
@@ -557,14 +559,14 @@ void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
     auto smem_of = [&](int nst) { return 256 + T::ring_bytes(nst) + (int)w.nb * 64 + 256; };
     if (smem_of(SST_MAX) > smem_set) {
         const int want = smem_of(SST_MAX) < 227 * 1024 ? smem_of(SST_MAX) : 227 * 1024;
-        B200_CHECK(cudaFuncSetAttribute(mmv_fused_kernel<TYPE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        B200_CHECK(cudaFuncSetAttribute(mmv_fused_kernel<TYPE, EPI, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
         smem_set = smem_of(SST_MAX);
     }
     auto it = occ_by_nb.find((int)w.nb);
     if (it == occ_by_nb.end()) {                                          // CTAs per SM for every ring depth at this activation length
         std::array<int, SST_MAX + 1> o{};
         for (int nst = 2; nst <= SST_MAX; nst++)
-            if (smem_of(nst) <= 227 * 1024) B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[nst], mmv_fused_kernel<TYPE, EPI>, STHREADS, smem_of(nst)));
+            if (smem_of(nst) <= 227 * 1024) B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[nst], mmv_fused_kernel<TYPE, EPI, TP>, STHREADS, smem_of(nst)));
         it = occ_by_nb.emplace((int)w.nb, o).first;
     }
     const std::array<int, SST_MAX + 1> &occ = it->second;
@@ -582,7 +584,16 @@ void launch_mmv(const QWeight &w, MmvArgs A, cudaStream_t st) {
     A.nst = nst;
     { static int pe = -1; if (pe < 0) { const char *e = getenv("B200_PDL_EARLY"); pe = e ? atoi(e) : 1; } A.pdl_early = pe; }
     const int64_t slots = (int64_t)sms * occ[nst];
-    launch_k<1>(mmv_fused_kernel<TYPE, EPI>, dim3((unsigned)(groups < slots ? groups : slots)), dim3(STHREADS), (size_t)smem_of(nst), st, w, A);
+    launch_k<1>(mmv_fused_kernel<TYPE, EPI, TP>, dim3((unsigned)(groups < slots ? groups : slots)), dim3(STHREADS), (size_t)smem_of(nst), st, w, A);
+}
+
+// dynamic shared memory opt-in of the cluster attention kernel: one high-water mark for both instantiations (the attribute is per function, not per caller)
+static void attn_fused_reserve(size_t bytes) {
+    static size_t set = 48 * 1024;
+    if (bytes <= set) return;
+    B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    set = bytes;
 }
 
 // tensor-parallel helpers (tp.cuh).  spread: the embedding row every rank computed for itself -> the X exchange buffer's unit form (stamp 0);
@@ -607,12 +618,13 @@ __global__ void tp_bump_kernel() {
     if (threadIdx.x == 0) *T.epoch = *(volatile unsigned *)T.epoch + 1;
 }
 
-template <int TYPE>
+template <int TYPE, bool TP>
 void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers, int n_kv_bucket, int4 *xpack_a, cudaStream_t st, int *launches) {
     const int q81 = has_min(TYPE) ? 1 : 0, off = TYPE == T_Q5_0 ? 16 : 0, s16 = TYPE == T_Q4_0 ? 1 : 0;
     const int e = P.e, f = P.f;
     const TpCtx &T = P.tp;
-    const bool tp = T.world > 1;
+    constexpr bool tp = TP;
+    B200_ASSERT(tp == (T.world > 1));
     const int e_loc = tp ? P.e_loc : e;
     // layer stamps (tp.cuh): X carries stamp il when it enters layer il (0 = the embedding), il + 1 when layer il leaves it; FF / XD / XF of layer il carry il + 1
     auto ts = [&](int in_buf, unsigned in_v, int add_buf, unsigned add_v, int out_buf, unsigned out_v) {
@@ -630,19 +642,18 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     const size_t fa_smem = (((size_t)nlay * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (nlay + 32) * 2;
     const bool fused_attn = (fused_env || tp) && P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024;
     B200_ASSERT(fused_attn || !tp);                              // the tensor-parallel exchange lives in the fused attention kernel's epilogue
-    static size_t fa_set = 48 * 1024;
-    if (fused_attn && fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
+    if (fused_attn) attn_fused_reserve(fa_smem);
     const size_t sv_smem = (size_t)P.n_ctx * 6 + 32 * KC * 2 + 32 * 32 * 2;
     static size_t sv_set = 48 * 1024;
     if (sv_smem > sv_set) { B200_CHECK(cudaFuncSetAttribute(attn_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sv_smem)); sv_set = sv_smem; }
     for (int il = 0; il < P.n_layer; il++) {
         const DecodeLayer &L = layers[il];
         const unsigned v = (unsigned)il + 1;                     // flag value of this layer's exchanges (tp.cuh)
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(),
+        launch_k(norm_pack_kernel<TP>, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(),
                  ts(TPB_X, (unsigned)il, -1, 0, -1, 0)); n++;
         MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e_loc; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
-        A.prof = pr(); launch_mmv<TYPE, EPI_QKV>(L.wqkv, A, st); n++;
+        A.prof = pr(); launch_mmv<TYPE, EPI_QKV, TP>(L.wqkv, A, st); n++;
         if (fused_attn) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(P.n_head * (P.hd / 32)); cfg.blockDim = dim3(ATH); cfg.dynamicSmemBytes = fa_smem; cfg.stream = st;
@@ -652,7 +663,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
             at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
-            B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
+            B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel<TP>, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
                                           (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head_kv, P.gqa, P.n_ctx, nlay, q81, off, s16, pr(),
                                           ts(-1, 0, -1, 0, TPB_XD, v), tp ? P.head0 : 0));
             n++;
@@ -665,20 +676,20 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
         }
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;
         Bo.ts = ts(TPB_XD, v, TPB_X, (unsigned)il, TPB_FF, v); Bo.row0 = tp ? P.row0_e : 0;
-        Bo.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.wo, Bo, st); n++;
-        launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), ts(TPB_FF, v, -1, 0, -1, 0)); n++;
+        Bo.prof = pr(); launch_mmv<TYPE, EPI_RES, TP>(L.wo, Bo, st); n++;
+        launch_k(norm_pack_kernel<TP>, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), ts(TPB_FF, v, -1, 0, -1, 0)); n++;
         MmvArgs C{}; C.xpack = xpack_a; C.xpack_out = P.xpack_f; C.lut_silu = P.lut_silu; C.q81 = q81; C.off = off; C.scale16 = s16;
         C.ts = ts(-1, 0, -1, 0, TPB_XF, v); C.row0 = tp ? P.row0_w13 : 0;
-        C.prof = pr(); launch_mmv<TYPE, EPI_SILU>(L.w13, C, st); n++;
+        C.prof = pr(); launch_mmv<TYPE, EPI_SILU, TP>(L.w13, C, st); n++;
         MmvArgs D{}; D.xpack = P.xpack_f; D.dst = P.x; D.addend = P.ff;
         D.ts = ts(TPB_XF, v, TPB_FF, v, TPB_X, v); D.row0 = tp ? P.row0_e : 0;
-        D.prof = pr(); launch_mmv<TYPE, EPI_RES>(L.w2, D, st); n++;
+        D.prof = pr(); launch_mmv<TYPE, EPI_RES, TP>(L.w2, D, st); n++;
     }
-    launch_k(norm_pack_kernel, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(),
+    launch_k(norm_pack_kernel<TP>, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(),
              ts(TPB_X, (unsigned)P.n_layer, -1, 0, -1, 0)); n++;
     MmvArgs Z{}; Z.xpack = xpack_a; Z.dst = P.logits; Z.addend = nullptr; Z.n_past_inc = P.n_past;
     Z.ts = ts(-1, 0, -1, 0, TPB_LOGITS, 0); Z.row0 = tp ? P.row0_v : 0;
-    Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS>(P.output, Z, st); n++;
+    Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS, TP>(P.output, Z, st); n++;
     if (tp) {                                                    // gathered logits -> the plain array the host reads; then the epoch moves on
         launch_k(tp_collect_kernel, dim3((P.n_vocab_full + 255) / 256), dim3(256), 0, st, P.logits, P.n_vocab_full); n++;
         launch_k(tp_bump_kernel, dim3(1), dim3(32), 0, st); n++;
@@ -781,8 +792,7 @@ void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n
     const int nlay = (n_kv_bucket + 63) / 64 * 64;
     const size_t fa_smem = (((size_t)nlay * 6 + (size_t)P.hd * 2 + 127) & ~(size_t)127) + (size_t)32 * (nlay + 32) * 2;
     B200_ASSERT(P.hd % 32 == 0 && P.hd <= 128 && P.n_ctx % 8 == 0 && fa_smem <= 227 * 1024 && e <= 8192);
-    static size_t fa_set = 48 * 1024;
-    if (fa_smem > fa_set) { B200_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem)); fa_set = fa_smem; }
+    attn_fused_reserve(fa_smem);
     const dim3 ln_grid((e / 4 + 255) / 256);
     const TpSync S{};
     for (int il = 0; il < P.n_layer; il++) {
@@ -801,7 +811,7 @@ void neox_ops_t(const NeoxParams &P, const std::vector<NeoxLayer> &layers, int n
             at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 2 : 1;
-            B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
+            B200_CHECK(cudaLaunchKernelEx(&cfg, attn_fused_kernel<false>, (const float *)P.q, (const __half *)L.K, (const __half *)L.V, P.xpack_d, (const int *)P.n_past,
                                           (const uint16_t *)P.lut_exp, P.kq_scale, P.hd, P.n_head, P.n_head, e, P.n_ctx, nlay, q81, off, s16,
                                           (unsigned long long *)nullptr, S, 0));                                                           // :250-298
             n++;
@@ -846,12 +856,13 @@ void decode_set_tp(const TpCtx &T, cudaStream_t st) {
 
 // Enqueue one decode step (position read from *P.n_past on the device) on `st`.  n_kv_bucket >= n_past + 1 sizes the KQ grid.
 void decode_ops_enqueue(const DecodeParams &P, const std::vector<DecodeLayer> &layers, int wtype, int n_kv_bucket, int4 *xpack_a, cudaStream_t st, int *launches) {
+    const bool tp = P.tp.world > 1;
     switch (wtype) {
-        case T_Q4_0: decode_ops_t<T_Q4_0>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
-        case T_Q4_1: decode_ops_t<T_Q4_1>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
-        case T_Q5_0: decode_ops_t<T_Q5_0>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
-        case T_Q5_1: decode_ops_t<T_Q5_1>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
-        case T_Q8_0: decode_ops_t<T_Q8_0>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
+        case T_Q4_0: if (tp) decode_ops_t<T_Q4_0, true>(P, layers, n_kv_bucket, xpack_a, st, launches); else decode_ops_t<T_Q4_0, false>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
+        case T_Q4_1: if (tp) decode_ops_t<T_Q4_1, true>(P, layers, n_kv_bucket, xpack_a, st, launches); else decode_ops_t<T_Q4_1, false>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
+        case T_Q5_0: if (tp) decode_ops_t<T_Q5_0, true>(P, layers, n_kv_bucket, xpack_a, st, launches); else decode_ops_t<T_Q5_0, false>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
+        case T_Q5_1: if (tp) decode_ops_t<T_Q5_1, true>(P, layers, n_kv_bucket, xpack_a, st, launches); else decode_ops_t<T_Q5_1, false>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
+        case T_Q8_0: if (tp) decode_ops_t<T_Q8_0, true>(P, layers, n_kv_bucket, xpack_a, st, launches); else decode_ops_t<T_Q8_0, false>(P, layers, n_kv_bucket, xpack_a, st, launches); break;
         default: B200_ASSERT(!"decode_ops_enqueue: unsupported weight type");
     }
 }

@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t tp_get(const TpCtx &T, int buf, int64_t unit
     const uint2 *src = (const uint2 *)(T.peer[T.rank] + T.off[buf]) + unit;
     uint32_t v, t;
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
-    if (t == tag || T.nowait) return v;
+    if (t == tag || T.nowait || *(volatile unsigned *)(T.epoch + 1)) return v;      // after the first timeout nothing waits any more: the session is dead, the host reports it
     const long long t0 = clock64();
     do {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
@@ -76,6 +76,7 @@ __device__ __forceinline__ uint4 tp_ld2(const TpCtx &T, int buf, int64_t pair) {
     return v;
 }
 __device__ __forceinline__ void tp_fix2(const TpCtx &T, int buf, int64_t pair, unsigned tag, uint4 &v) {     // payloads end up in v.x and v.z
+    if (T.nowait) return;
     if (v.y != tag) v.x = tp_get(T, buf, 2 * pair, tag);
     if (v.w != tag) v.z = tp_get(T, buf, 2 * pair + 1, tag);
 }
