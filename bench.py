@@ -337,13 +337,15 @@ def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
         barrier()
     clocks = clk.summary()
     assert np.isfinite(logits).all()
-    ms_nowait = None
+    ms_nowait = ms_local = None
     if world > 1:                                                 # the same schedule without the flag waits: what the exchange costs beyond compute + stores
         assert L.b200_session_tp_set_nowait(sess._s, 1) == 0
         ms_nowait = timed(steps)
+        assert L.b200_session_tp_set_nowait(sess._s, 2) == 0       # ... and with every store kept local: compute alone
+        ms_local = timed(steps)
         assert L.b200_session_tp_set_nowait(sess._s, 0) == 0
         assert sess.timeouts == 0, "a tensor-parallel flag wait timed out"
-    vals = allmax(ms_dev, ms_e2e, ms_nowait if ms_nowait is not None else 0.0)
+    vals = allmax(ms_dev, ms_e2e, ms_nowait if ms_nowait is not None else 0.0, ms_local if ms_local is not None else 0.0)
     ms_dev, ms_e2e = vals[0], vals[1]
     if rank != 0:
         if dist is not None:
@@ -376,8 +378,11 @@ def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
     }
     if world > 1:
         line["exchange"] = {"per_token": 4 * hp["n_layer"] + 1, "gathered_bytes_per_token_per_gpu": exch, "nvlink_bytes_per_token_per_gpu_sent": exch * (world - 1) // world,
-                            "ms_per_step_without_flag_waits": vals[2] / steps, "exposed_wait_share_of_step": max(0.0, 1.0 - vals[2] / ms_dev),
-                            "note": "time with the flag waits skipped (garbage results) = compute + peer stores; the difference is what waiting for the slowest rank's slices costs"}
+                            "ms_per_step_without_tag_waits": vals[2] / steps, "ms_per_step_local_stores_only": vals[3] / steps,
+                            "exposed_wait_share_of_step": max(0.0, 1.0 - vals[2] / ms_dev), "peer_store_share_of_step": max(0.0, (vals[2] - vals[3]) / ms_dev),
+                            "relaxed_grid_waits": os.environ.get("B200_TP_RELAX", "1") != "0",
+                            "note": "same schedule with the tag waits skipped (garbage results) = compute + peer stores, and with every store kept local = compute alone; "
+                                    "the differences are what waiting for the slowest rank's slices and what the NVLink stores cost"}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -167,7 +167,8 @@ void b200_session_free(b200_session *s);
 int  b200_session_tp_handle(b200_session *s, void *handle_out64);
 int  b200_session_tp_connect(b200_session *s, const void *handles_by_rank);
 int32_t b200_session_tp_timeouts(b200_session *s);
-/* measurement aid: nowait != 0 skips the flag waits (garbage results; time = compute + peer stores), to size the exchange's share of a token */
+/* measurement aid: nowait 1 skips the tag waits (garbage results; time = compute + peer stores), 2 also keeps every store local (time = compute alone):
+ * sizes the exchange's share of a token */
 int  b200_session_tp_set_nowait(b200_session *s, int32_t nowait);
 
 /* stream handle (cudaStream_t) on which everything above is ordered -- for CUDA-event timing from the host side */

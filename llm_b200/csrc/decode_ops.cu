@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
-    pdl_wait();
+    // Tensor-parallel: the row arrives as tagged units and the records this kernel overwrites were last read by a mat-vec whose outputs the producers of
+    // those units needed (tp.cuh): nothing here depends on the predecessor grid having COMPLETED, only on its units -- do not wait for its peer stores to be acknowledged.
+    if (!(TP && T.relax)) pdl_wait();
     constexpr bool tp = TP;                                    // tensor-parallel: the row is an array of {value, tag} units filled by every rank (tp.cuh)
     const unsigned tag = tp ? tp_tag(T, S.in_v) : 0u;
 
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         if (pdl_early) pdl_trigger();                           // every byte of this CTA is requested: let the successor's CTAs take the free slots
         return;
     }
-    pdl_wait();
+    if (!(TP && c_tp.relax && A.ts.in_buf >= 0)) pdl_wait();    // records and addend arrive as tagged units: no dependence on the predecessor's completion (tp.cuh)
     if (TP && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
         const unsigned tag = tp_tag(c_tp, A.ts.in_v);
         const int npair = (int)w.nb * 8;                        // a 16-byte record = 4 units = 2 pairs

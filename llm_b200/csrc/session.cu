@@ -556,6 +556,7 @@ static b200_session *start_session_tp(b200_session *s) {
     TpCtx &T = s->dp.tp;
     T = TpCtx();
     T.world = G; T.rank = r; T.vmul = (unsigned)hp.n_layer + 1;
+    { const char *e = getenv("B200_TP_RELAX"); T.relax = e ? atoi(e) : 1; }
     size_t off = 0;
     auto piece = [&](size_t units) { const size_t o = off; off += (units * 8 + 255) & ~(size_t)255; return (uint32_t)o; };
     T.off[TPB_X] = piece(e); T.off[TPB_FF] = piece(e); T.off[TPB_XD] = piece((e / QK) * 16); T.off[TPB_XF] = piece((f / QK) * 16); T.off[TPB_LOGITS] = piece(V);
@@ -829,7 +830,7 @@ int b200_session_tp_connect(b200_session *s, const void *handles_by_rank) {
 int b200_session_tp_set_nowait(b200_session *s, int32_t nowait) {     // measurement aid: the captured graphs carry the flag, so they are dropped
     if (!s || !s->tp_slab) return B200_ERR_BAD_ARG;
     B200_CHECK(cudaStreamSynchronize(rt().stream));
-    s->dp.tp.nowait = nowait ? 1 : 0;
+    s->dp.tp.nowait = nowait < 0 ? 0 : nowait > 2 ? 2 : nowait;
     decode_set_tp(s->dp.tp, rt().stream);
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.second);
     s->graphs.clear();

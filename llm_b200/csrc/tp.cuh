@@ -29,7 +29,10 @@ struct TpCtx {                 // kernel argument (POD); world == 1: single GPU,
     unsigned *epoch = nullptr;     // local: [0] tokens decoded so far, [1] number of polls that timed out (a peer died)
     uint32_t off[TPB_COUNT] = {};  // byte offsets of the buffers (arrays of 8-byte units) inside a slab
     unsigned vmul = 1;             // n_layer + 1
-    int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): accept whatever a unit holds -- results are garbage, the time is compute + stores
+    int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): 1 = accept whatever a unit holds -- results are garbage, the time is compute + stores;
+                                   // 2 = additionally store to the local slab only: the time is compute alone
+    int relax = 1;                 // kernels whose every dependence on their predecessor travels through tagged units do not wait for the predecessor grid
+                                   // to COMPLETE (griddepcontrol.wait also waits for its peer stores to be acknowledged across NVLink); B200_TP_RELAX=0 restores the waits
 };
 
 // what one kernel instance reads / writes (baked into the CUDA graph; the epoch is read from device memory)
@@ -44,6 +47,7 @@ __device__ __forceinline__ unsigned tp_tag(const TpCtx &T, unsigned v) { return 
 __device__ __forceinline__ void tp_put(const TpCtx &T, int buf, int64_t unit, uint32_t payload, unsigned tag) {
 #pragma unroll 1
     for (int p = 0; p < T.world; p++) {
+        if (T.nowait == 2 && p != T.rank) continue;
         uint2 *dst = (uint2 *)(T.peer[p] + T.off[buf]) + unit;
         asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(payload), "r"(tag) : "memory");
     }
