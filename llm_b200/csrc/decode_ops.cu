@@ -99,6 +99,10 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     double s = 0.0;
     constexpr int U = 4;
+    if (tp && T.relax) {                                        // launched ahead of the data: warp 0 watches a sample of the row, the others sleep on the barrier
+        if (warp == 0) tp_wait_sample(T, S.in_buf, (int64_t)e, tag, lane);
+        __syncthreads();
+    }
     for (int i0 = tid; i0 < nv; i0 += 256 * U) {
         float4 v[U];
         if (!tp) {
@@ -177,6 +181,10 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
     if (!(TP && c_tp.relax && A.ts.in_buf >= 0)) pdl_wait();    // records and addend arrive as tagged units: no dependence on the predecessor's completion (tp.cuh)
     if (TP && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
         const unsigned tag = tp_tag(c_tp, A.ts.in_v);
+        if (c_tp.relax) {                                       // launched ahead of the data: warp 0 watches a sample, the others sleep on the barrier
+            if (tid < 32) tp_wait_sample(c_tp, A.ts.in_buf, (int64_t)w.nb * 16, tag, tid);
+            compute_sync();
+        }
         const int npair = (int)w.nb * 8;                        // a 16-byte record = 4 units = 2 pairs
         constexpr int U = 8;                                    // 16-byte loads in flight per thread
         for (int i0 = tid; i0 < npair; i0 += SCOMPUTE * U) {

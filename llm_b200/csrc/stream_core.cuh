@@ -30,6 +30,13 @@ template <int TYPE, int ROWS = SR, int CB = SCB> struct St {
     __host__ __device__ static constexpr int ring_bytes(int nst) { return nst * STAGE_BYTES; }
 };
 
+// int -> float without the conversion unit: the block dots start from the accumulator seed 0x4B400000 (the bits of 12582912.0f = 1.5 * 2^23), so the
+// integer result, read as a float, is exactly 12582912 + s for |s| < 2^22 (here |s| <= 4 * 128 * 127 + seeds), and one FADD on the FMA pipe returns
+// exactly (float)s.  The I2F of the straightforward form runs on the quarter-rate XU pipe, which measured ~50 % busy in the mat-vec steady state
+// (profiles/r01h_mmv_fused.ncu-rep: sm__inst_executed_pipe_xu 37 % of the elapsed time including the ramp) with the FMA pipe at 15 %.
+constexpr int I2F_MAGIC = 0x4B400000;
+__device__ __forceinline__ float i2f_magic(int biased) { return __fadd_rn(__int_as_float(biased), -12582912.0f); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
@@ -143,14 +150,14 @@ __device__ __forceinline__ void consume_matvec(const QWeight &w, const int4 *sx,
                 else dw = __half2float(*(const __half *)(drow + b * T::DM));
                 int s_lo, s_hi;
                 if (TYPE == T_Q8_0) {
-                    s_lo = __dp4a(*(const int *)(qrow + b * T::QS + 4 * wd), xp.x, 0);
-                    s_hi = __dp4a(*(const int *)(qrow + b * T::QS + 16 + 4 * wd), xp.y, 0);
+                    s_lo = __dp4a(*(const int *)(qrow + b * T::QS + 4 * wd), xp.x, I2F_MAGIC);
+                    s_hi = __dp4a(*(const int *)(qrow + b * T::QS + 16 + 4 * wd), xp.y, I2F_MAGIC);
                 } else if (TYPE == T_Q4_0) {
                     // (q - 8) as a 4-bit two's complement value is q ^ 8; parked in the HIGH nibble of each byte it reads as 16*(q-8):
                     // the dp4a result is exactly 16 * sum (q-8) x, and the 1/16 rides (exactly, a power of two) in the packed d_x.
                     const uint32_t q = *(const uint32_t *)(qrow + b * T::QS + 4 * wd);
-                    s_lo = __dp4a((int)(((q << 4) ^ 0x80808080u) & 0xF0F0F0F0u), xp.x, 0);
-                    s_hi = __dp4a((int)((q ^ 0x88888888u) & 0xF0F0F0F0u), xp.y, 0);
+                    s_lo = __dp4a((int)(((q << 4) ^ 0x80808080u) & 0xF0F0F0F0u), xp.x, I2F_MAGIC);
+                    s_hi = __dp4a((int)((q ^ 0x88888888u) & 0xF0F0F0F0u), xp.y, I2F_MAGIC);
                 } else {
                     const uint32_t q = *(const uint32_t *)(qrow + b * T::QS + 4 * wd);
                     uint32_t l = q & 0x0F0F0F0Fu, h = (q >> 4) & 0x0F0F0F0Fu;
@@ -160,14 +167,14 @@ __device__ __forceinline__ void consume_matvec(const QWeight &w, const int4 *sx,
                         h |= spread4_to_bit4(qh >> (16 + 4 * wd));
                     }
                     // Q5_0: the -16 offset of every value is pre-multiplied into the accumulator seeds (exact integers); Q4_1/Q5_1: no offset
-                    const int seed_lo = TYPE == T_Q5_0 ? (int)(short)(xp.z & 0xffff) : 0;
-                    const int seed_hi = TYPE == T_Q5_0 ? (xp.z >> 16) : 0;
+                    const int seed_lo = TYPE == T_Q5_0 ? (int)(short)(xp.z & 0xffff) + I2F_MAGIC : I2F_MAGIC;
+                    const int seed_hi = TYPE == T_Q5_0 ? (xp.z >> 16) + I2F_MAGIC : I2F_MAGIC;
                     s_lo = __dp4a((int)l, xp.x, seed_lo);
                     s_hi = __dp4a((int)h, xp.y, seed_hi);
                 }
                 const float d = __fmul_rn(dw, __int_as_float(xp.w));
-                a_lo = __fmaf_rn(d, (float)s_lo, a_lo);
-                a_hi = __fmaf_rn(d, (float)s_hi, a_hi);
+                a_lo = __fmaf_rn(d, i2f_magic(s_lo), a_lo);
+                a_hi = __fmaf_rn(d, i2f_magic(s_hi), a_hi);
                 if (T::MIN) summs = __fmaf_rn(mw, __int_as_float(xp.z), summs);
             }
             __syncwarp();

@@ -65,11 +65,19 @@ __device__ __forceinline__ uint32_t tp_get(const TpCtx &T, int buf, int64_t unit
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
     if (t == tag || T.nowait || *(volatile unsigned *)(T.epoch + 1)) return v;      // after the first timeout nothing waits any more: the session is dead, the host reports it
     const long long t0 = clock64();
+    unsigned ns = 32;
     do {
+        __nanosleep(ns); if (ns < 512) ns *= 2;                  // back off: thousands of spinning threads would otherwise flood L2 while the producers still stream weights
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
         if (clock64() - t0 > 6000000000LL) { atomicAdd(T.epoch + 1, 1u); break; }        // a peer is gone: do not hang the GPU, count it (b200_session_tp_timeouts)
     } while (t != tag);
     return v;
+}
+// One warp waits for a spread sample of a buffer (32 units, one per lane) before the CTA gathers it: a consumer that was launched ahead of its data
+// (TpCtx::relax) then polls 32 words per CTA with back-off instead of re-reading the whole buffer from L2 until it is complete.
+__device__ __forceinline__ void tp_wait_sample(const TpCtx &T, int buf, int64_t nunits, unsigned tag, int lane) {
+    const int64_t unit = nunits <= 32 ? (lane < nunits ? lane : nunits - 1) : (int64_t)lane * (nunits - 1) / 31;
+    (void)tp_get(T, buf, unit, tag);
 }
 // Two units per 16-byte load, for consumers that read many units: issue ALL the loads first (tp_ld2), then check the tags (tp_fix2) -- the polling branch
 // of tp_get serialises a thread's loads at one L2 round trip each (measured: 6.8 us to gather w2's input records that way, profiles/r02_notes.md).
