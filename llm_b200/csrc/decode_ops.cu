@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     pdl_trigger();                                              // 4 CTAs: the next mat-vec fits beside this kernel and streams its first stages meanwhile
     // Tensor-parallel: the row arrives as tagged units and the records this kernel overwrites were last read by a mat-vec whose outputs the producers of
     // those units needed (tp.cuh): nothing here depends on the predecessor grid having COMPLETED, only on its units -- do not wait for its peer stores to be acknowledged.
-    if (!(TP && T.relax)) pdl_wait();
+    if (!(TP && (T.relax & 1))) pdl_wait();
     constexpr bool tp = TP;                                    // tensor-parallel: the row is an array of {value, tag} units filled by every rank (tp.cuh)
     const unsigned tag = tp ? tp_tag(T, S.in_v) : 0u;
 
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     double s = 0.0;
     constexpr int U = 4;
-    if (tp && T.relax) {                                        // launched ahead of the data: warp 0 watches a sample of the row, the others sleep on the barrier
+    if (tp && (T.relax & 1)) {                                  // launched ahead of the data: warp 0 watches a sample of the row, the others sleep on the barrier
         if (warp == 0) tp_wait_sample(T, S.in_buf, (int64_t)e, tag, lane);
         __syncthreads();
     }
@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, co
         if (pdl_early) pdl_trigger();                           // every byte of this CTA is requested: let the successor's CTAs take the free slots
         return;
     }
-    if (!(TP && c_tp.relax && A.ts.in_buf >= 0)) pdl_wait();    // records and addend arrive as tagged units: no dependence on the predecessor's completion (tp.cuh)
+    if (!(TP && (c_tp.relax & 2) && A.ts.in_buf >= 0)) pdl_wait();    // records and addend arrive as tagged units: no dependence on the predecessor's completion (tp.cuh)
     if (TP && A.ts.in_buf >= 0) {                 // tensor-parallel: the input records arrive from every rank as {word, tag} units (tp.cuh)
         const unsigned tag = tp_tag(c_tp, A.ts.in_v);
-        if (c_tp.relax) {                                       // launched ahead of the data: warp 0 watches a sample, the others sleep on the barrier
+        if (c_tp.relax & 2) {                                   // launched ahead of the data: warp 0 watches a sample, the others sleep on the barrier
             if (tid < 32) tp_wait_sample(c_tp, A.ts.in_buf, (int64_t)w.nb * 16, tag, tid);
             compute_sync();
         }

@@ -31,8 +31,10 @@ struct TpCtx {                 // kernel argument (POD); world == 1: single GPU,
     unsigned vmul = 1;             // n_layer + 1
     int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): 1 = accept whatever a unit holds -- results are garbage, the time is compute + stores;
                                    // 2 = additionally store to the local slab only: the time is compute alone
-    int relax = 1;                 // kernels whose every dependence on their predecessor travels through tagged units do not wait for the predecessor grid
-                                   // to COMPLETE (griddepcontrol.wait also waits for its peer stores to be acknowledged across NVLink); B200_TP_RELAX=0 restores the waits
+    int relax = 1;                 // bit 0: the norm kernels, bit 1: the mat-vecs fed by exchanged records -- kernels whose every dependence on their predecessor
+                                   // travels through tagged units do not wait for the predecessor grid to COMPLETE (griddepcontrol.wait also waits for its
+                                   // peer stores to be acknowledged across NVLink).  Measured (profiles/r02_notes.md): 1 is best -- a relaxed mat-vec grid becomes
+                                   // resident early and its pollers take issue slots and L2 bandwidth from the producers.  B200_TP_RELAX overrides.
 };
 
 // what one kernel instance reads / writes (baked into the CUDA graph; the epoch is read from device memory)
