@@ -105,5 +105,6 @@ def lib():
     L.b200_op_quantize_act.argtypes = [i32, vp, i64, i64, vp, vp, vp]
     L.b200_op_quantize_weights.argtypes = [i32, vp, i64, i64, vp]
     L.b200_op_mul_mat.argtypes = [i32, vp, i64, i64, vp, i64, vp, i32]
+    L.b200_op_quantize_q8_K.argtypes = [vp, i64, i64, vp]
     _lib = L
     return L

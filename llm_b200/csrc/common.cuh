@@ -28,21 +28,26 @@
 namespace b200 {
 
 // enum ggml_type values (LC/ggml.h:262-285)
-enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q8_1 = 9, T_I8 = 16, T_I16 = 17, T_I32 = 18 };
+enum : int { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q8_1 = 9, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
+              T_Q8_K = 15, T_I8 = 16, T_I16 = 17, T_I32 = 18 };
 
 constexpr int QK = 32;  // elements per quant block for all five formats (LC/ggml.c:895-940)
 
 __host__ __device__ inline bool is_quant(int t) { return t == T_Q4_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_Q8_0; }
+// K-quants with kernels here (kquants.cu): 256-element super-blocks kept in HBM exactly as GGML lays them out (LC/k_quants.h:60-110)
+__host__ __device__ inline bool is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K; }
+__host__ __device__ inline int kquant_block_bytes(int t) { return t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : 0; }
 // bytes per GGML block as laid out in files / host memory
 __host__ __device__ inline int ggml_block_bytes(int t) {
-    switch (t) { case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24; case T_Q8_0: return 34; case T_Q8_1: return 40; }
+    switch (t) { case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24; case T_Q8_0: return 34; case T_Q8_1: return 40;
+                 case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144; case T_Q5_K: return 176; case T_Q6_K: return 210; case T_Q8_K: return 292; }
     return 0;
 }
 __host__ __device__ inline size_t ggml_type_size(int t) {  // bytes per block (block = 1 element for scalar types)
     switch (t) { case T_F32: case T_I32: return 4; case T_F16: case T_I16: return 2; case T_I8: return 1; }
     return (size_t)ggml_block_bytes(t);
 }
-__host__ __device__ inline int ggml_blck_size(int t) { return is_quant(t) || t == T_Q8_1 ? QK : 1; }
+__host__ __device__ inline int ggml_blck_size(int t) { return (t >= T_Q2_K && t <= T_Q8_K) ? 256 : (is_quant(t) || t == T_Q8_1) ? QK : 1; }
 // activation quantization format paired with each weight format (type_traits[].vec_dot_type, LC/ggml.c:1645-1737)
 __host__ __device__ inline int vec_dot_type(int t) { return (t == T_Q4_1 || t == T_Q5_1) ? T_Q8_1 : T_Q8_0; }
 __host__ __device__ inline bool has_min(int t) { return t == T_Q4_1 || t == T_Q5_1; }

@@ -61,6 +61,12 @@ bool mmv_exact_stream_supported(const QWeight &w);
 void quantize_act_pack(int wtype, const float *x, int4 *pack, int64_t K, cudaStream_t st);
 void mul_mat_vec_q_exact_stream(const QWeight &w, const int4 *xpack, float *dst, const float *addend, cudaStream_t st);
 
+// ---- kquants.cu : Q4_K / Q5_K / Q6_K weights x Q8_K activations, bit-exact with ggml_vec_dot_q*_K_q8_K (AVX2 build) -------------------------
+size_t q8k_bytes(int64_t K, int64_t B);
+void quantize_act_q8k(const float *x, int64_t ldx, void *y, int64_t K, int64_t B, cudaStream_t st);       // quantize_row_q8_K of every src1 row -> block_q8_K
+void mul_mat_kq_exact(int type, const void *w_raw, const void *xq8k, float *dst, int64_t ldd, int64_t K, int64_t N, int64_t B, const float *addend, int64_t lda,
+                      cudaStream_t st);                                                                   // w_raw: N rows of K/256 GGML super-blocks, as in the file
+
 // ---- synth.cu : seeded synthetic tensors generated in HBM (bench / tests) ------------------------------------------------------------
 void synth_qweight(const QWeight &w, uint64_t seed, cudaStream_t st);
 void synth_gain(float *g, int64_t n, uint64_t seed, cudaStream_t st);                       // 1 + 0.1 N(0,1)

@@ -190,6 +190,29 @@ void op_mul_mat(const ggml_tensor *src0, const ggml_tensor *src1, ggml_tensor *d
         dst_finish(dst, d);
         return;
     }
+    if (is_kquant(src0->type)) {
+        // Q4_K / Q5_K / Q6_K: the super-blocks stay in GGML's own layout (transform_tensor uploaded them as they are); quantize_row_q8_K + vec_dot order of the AVX2 build
+        B200_ASSERT(src0->ne[2] == 1 && src0->ne[3] == 1 && is_contiguous(src0) && is_contiguous(dst));
+        B200_ASSERT(src1->nb[0] == 4 && src1->ne[2] * src1->ne[3] == 1 || is_contiguous(src1));
+        const int64_t K = src0->ne[0], N = src0->ne[1], B = nrows(src1);
+        B200_ASSERT(K % 256 == 0);
+        const void *wraw;
+        if (on_device(src0)) { Extra *e = (Extra *)src0->extra; B200_ASSERT(e && e->data); wraw = e->data; }
+        else {
+            const size_t raw_bytes = (size_t)N * (K / 256) * kquant_block_bytes(src0->type);
+            void *raw = R.op_arena.get(raw_bytes, st);
+            B200_CHECK(cudaMemcpyAsync(raw, src0->data, raw_bytes, cudaMemcpyHostToDevice, st));
+            wraw = raw;
+        }
+        const float *x = (const float *)src_dev(src1);
+        float *d = (float *)dst_dev(dst);
+        const int64_t ldx = is_contiguous(src1) ? K : (int64_t)(src1->nb[1] / 4);
+        void *xq = R.op_arena.get(q8k_bytes(K, B), st);
+        quantize_act_q8k(x, ldx, xq, K, B, st);
+        mul_mat_kq_exact(src0->type, wraw, xq, d, N, K, N, B, nullptr, 0, st);
+        dst_finish(dst, d);
+        return;
+    }
     if (src0->type == B200_TYPE_F16) {
         B200_ASSERT(src0->nb[0] == 2 && src1->nb[0] == 4 && dst->nb[0] == 4);
         B200_ASSERT(src0->ne[3] == 1 && src1->ne[3] == 1);
@@ -402,6 +425,8 @@ void ggml_cuda_assign_buffers_force_inplace(struct ggml_tensor *tensor) { assign
 bool ggml_cuda_can_mul_mat(const struct ggml_tensor *src0, const struct ggml_tensor *src1, struct ggml_tensor *dst) {   // :3627-3642
     const int64_t ne10 = src1->ne[0], ne0 = dst->ne[0], ne1 = dst->ne[1];
     // F32/F16 host-resident weights are not on this backend's path (only the five block formats are): let the CPU keep them.
+    if (is_kquant(src0->type))
+        return src1->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32 && ne0 >= 32 && ne1 >= 32 && ne10 >= 32 && src0->ne[0] % 256 == 0 && src0->ne[2] == 1 && src0->ne[3] == 1;
     return is_quant(src0->type) && src1->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32 && ne0 >= 32 && ne1 >= 32 && ne10 >= 32 &&
            src0->ne[0] % 64 == 0 && src0->ne[2] == 1 && src0->ne[3] == 1;
 }

@@ -881,7 +881,36 @@ int b200_op_quantize_act(int32_t vdt, const float *x, int64_t K, int64_t B, int8
     return B200_OK;
 }
 
+int b200_op_quantize_q8_K(const float *x, int64_t K, int64_t B, void *blocks_out) {      // quantize_row_q8_K of B rows -> B * K/256 block_q8_K (292 bytes each)
+    if (!x || !blocks_out || K % 256) return B200_ERR_BAD_ARG;
+    Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
+    cudaStream_t st = R.stream;
+    float *dx = (float *)R.op_arena.get((size_t)B * K * 4, st);
+    void *xq = R.op_arena.get(q8k_bytes(K, B), st);
+    B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
+    quantize_act_q8k(dx, K, xq, K, B, st);
+    B200_CHECK(cudaMemcpyAsync(blocks_out, xq, q8k_bytes(K, B), cudaMemcpyDeviceToHost, st));
+    B200_CHECK(cudaStreamSynchronize(st));
+    return B200_OK;
+}
 int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, const float *x, int64_t B, float *dst, int32_t impl) {
+    if (is_kquant(wtype)) {                              // Q4_K / Q5_K / Q6_K: one exact kernel (kquants.cu); `impl` must be AUTO or EXACT
+        if (!w_ggml || !x || !dst || K % 256 || (impl != B200_MM_AUTO && impl != B200_MM_EXACT)) return B200_ERR_BAD_ARG;
+        Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
+        cudaStream_t st = R.stream;
+        const size_t raw_bytes = (size_t)N * (K / 256) * kquant_block_bytes(wtype);
+        void *raw = R.op_arena.get(raw_bytes, st);
+        float *dx = (float *)R.op_arena.get((size_t)B * K * 4, st);
+        float *dd = (float *)R.op_arena.get((size_t)B * N * 4, st);
+        void *xq = R.op_arena.get(q8k_bytes(K, B), st);
+        B200_CHECK(cudaMemcpyAsync(raw, w_ggml, raw_bytes, cudaMemcpyHostToDevice, st));
+        B200_CHECK(cudaMemcpyAsync(dx, x, (size_t)B * K * 4, cudaMemcpyHostToDevice, st));
+        quantize_act_q8k(dx, K, xq, K, B, st);
+        mul_mat_kq_exact(wtype, raw, xq, dd, N, K, N, B, nullptr, 0, st);
+        B200_CHECK(cudaMemcpyAsync(dst, dd, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+        B200_CHECK(cudaStreamSynchronize(st));
+        return B200_OK;
+    }
     if (!is_quant(wtype) || !w_ggml || !x || !dst || K % 64) return B200_ERR_BAD_ARG;
     Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
     cudaStream_t st = R.stream;

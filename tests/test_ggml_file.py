@@ -212,5 +212,5 @@ def test_k_quant_tensors_parse_like_the_reference(tmp_path):
     path = str(tmp_path / "kq.bin")
     _raw_file(path, tensors=[(1, b"q4k", 12, (256,), b"\0" * 144), (1, b"q6k", 14, (512,), b"\0" * 420), (1, b"q2k", 10, (256,), b"\0" * 84)])
     f = loader.GgmlFile(path)
-    infos = {t.name: t for t in f.tensors}
-    assert infos["q4k"].nbytes == 144 and infos["q6k"].nbytes == 420 and infos["q2k"].nbytes == 84
+    infos = {t["name"]: t for t in f.tensors()}
+    assert infos["q4k"]["nbytes"] == 144 and infos["q6k"]["nbytes"] == 420 and infos["q2k"]["nbytes"] == 84
