@@ -40,7 +40,7 @@ uint64_t data_size(int32_t type, uint64_t n) {
         case b200::T_F16: return n * 2;
         case b200::T_Q4_0: case b200::T_Q4_1: case b200::T_Q5_0: case b200::T_Q5_1: case b200::T_Q8_0: case b200::T_Q8_1:
             return n / b200::QK * (uint64_t)b200::ggml_block_bytes(type);
-        // K-quants (LC/k_quants.h, QK_K = 256): parsed and sized like the reference's loader does; the native sessions stream the five 32-element formats only (kquants.cu serves Q4_K/Q5_K/Q6_K per operator), so
+        // K-quants (LC/k_quants.h, QK_K = 256): parsed and sized like the reference's loader does; the native sessions stream the five 32-element formats only (kquants.cu serves Q2_K..Q6_K per operator), so
         // b200_llama_load_file reports the tensor by name instead of failing the whole parse (GGJT v3 "Q4_0" files of the vendored llama.cpp
         // quantizer carry output.weight as Q6_K, LC/llama.cpp:2938-2944)
         case 10: return n / 256 * 84;  case 11: return n / 256 * 110; case 12: return n / 256 * 144; case 13: return n / 256 * 176; case 14: return n / 256 * 210;

@@ -1,8 +1,8 @@
-// llm_b200/csrc/kquants.cu -- K-quant weights (256-element super-blocks, LC/k_quants.h:28-120): bit-exact mat-mul against Q8_K activations.
+// llm_b200/csrc/kquants.cu -- K-quant weights Q2_K .. Q6_K (256-element super-blocks, LC/k_quants.h:28-120): bit-exact mat-mul against Q8_K activations.
 //
-// Serves ggml_compute_forward_mul_mat (LC/ggml.c:10397-10586) when src0 is Q4_K / Q5_K / Q6_K: type_traits[] pairs them with
+// Serves ggml_compute_forward_mul_mat (LC/ggml.c:10397-10586) when src0 is Q2_K / Q3_K / Q4_K / Q5_K / Q6_K: type_traits[] pairs them with
 // vec_dot_type = Q8_K (LC/ggml.c:1700-1737), i.e. the INIT phase runs quantize_row_q8_K on every src1 row and the COMPUTE phase calls
-// ggml_vec_dot_q{4,5,6}_K_q8_K (LC/k_quants.c:2492, :3023, :3592) once per (weight row, src1 row).
+// ggml_vec_dot_q{2,3,4,5,6}_K_q8_K (LC/k_quants.c:1240, :1763, :2492, :3023, :3592) once per (weight row, src1 row).
 //
 // What "the reference's result" is (the x86 build of crates/ggml/sys/build.rs: -mavx2 -mfma -mf16c, QK_K = 256):
 //   * quantize_row_q8_K_reference (LC/k_quants.c:1133-1168): the FIRST element of largest magnitude gives iscale = -128/max, q = min(127, nearest_int(iscale*x)),
@@ -11,7 +11,8 @@
 //   * the AVX2 dot products keep 8 int32 lanes per super-block (lane L = bytes 4L..4L+3 of every 32-byte group, each group weighted by its 6-bit / 8-bit sub-block
 //     scale: all integer, exact) and ONE 8-lane f32 accumulator: acc_L = fma(d, (float)sumi_L, acc_L) per super-block in order, d = y.d * fp16(x.d); the result is
 //     hsum_float_8(acc) (LC/k_quants.c:1193-1199) plus the "mins" term: Q4_K keeps 4 f32 lanes acc_m[t] = fma(dmin, (float)prod[t], acc_m[t]) reduced as
-//     (m0+m2)+(m1+m3) (:2618-2620, :2652-2655); Q5_K a scalar summs = fma(dmin, (float)(prod0+..+prod3), summs) (:3157-3160; contracted, vfmadd231ss).
+//     (m0+m2)+(m1+m3) (:2618-2620, :2652-2655); Q5_K a scalar summs = fma(dmin, (float)(prod0+..+prod3), summs) (:3157-3160; contracted, vfmadd231ss);
+//     Q2_K folds its mins into the SAME 8 lanes first: acc_L = fma(dmin, (float)(m[2L] bsums[2L] + m[2L+1] bsums[2L+1]), acc_L) (:1346-1350).
 // One warp per (weight row, src1 row): lane = 8*part + L owns byte column L of two of the eight 32-byte groups; the integer partials meet by shuffles,
 // every lane then carries the f32 chain of its L.  This is a correctness-first kernel (weights re-read per src1 row through L2): the fused decode schedule
 // and the tensor-core prefill GEMMs serve the five classic formats only.
@@ -81,6 +82,8 @@ __device__ __forceinline__ int k4_scale(const uint8_t *q, int j) { return j < 4 
 __device__ __forceinline__ int k4_min(const uint8_t *q, int j) { return j < 4 ? (q[j + 4] & 63) : ((q[j + 4] >> 4) | ((q[j] >> 6) << 4)); }
 
 template <int TYPE> struct KQ;
+template <> struct KQ<T_Q2_K> { static constexpr int BYTES = 84, QS = 16, QH = 0; };      // scales[16] qs[64] d dmin   (LC/k_quants.h:34-39)
+template <> struct KQ<T_Q3_K> { static constexpr int BYTES = 110, QS = 32, QH = 0; };     // hmask[32] qs[64] scales[12] d (:52-57)
 template <> struct KQ<T_Q4_K> { static constexpr int BYTES = 144, QS = 16, QH = 0; };
 template <> struct KQ<T_Q5_K> { static constexpr int BYTES = 176, QS = 48, QH = 16; };
 template <> struct KQ<T_Q6_K> { static constexpr int BYTES = 210, QS = 0, QH = 128; };
@@ -99,7 +102,41 @@ __global__ void __launch_bounds__(128) mul_mat_kq_exact_kernel(const uint8_t *__
         const BlockQ8K *xb = xrow + i;
         const float yd = xb->d;
         int p;
-        if (TYPE == T_Q6_K) {
+        if (TYPE == T_Q2_K || TYPE == T_Q3_K) {
+            // 2-bit planes: group (j, k) = bits 2k of qs[32j ..] against q8[128j + 32k ..]; sub-block scale index 8j + 2k + (L >= 4) (get_scale_shuffle_q3k)
+            const int j = part >> 1;
+            float d;
+            uint32_t w, hm = 0;
+            if (TYPE == T_Q2_K) {
+                d = __fmul_rn(yd, h2f(wb + 80));
+                const float dmin = __fmul_rn(-yd, h2f(wb + 82));
+                const int prod = (int)(wb[2 * L] >> 4) * (int)xb->bsums[2 * L] + (int)(wb[2 * L + 1] >> 4) * (int)xb->bsums[2 * L + 1];
+                acc = __fmaf_rn(dmin, (float)prod, acc);              // the mins go into the SAME accumulator, before the quants (:1350)
+                w = *(const uint32_t *)(wb + 16 + 32 * j + 4 * L);
+            } else {
+                d = __fmul_rn(yd, h2f(wb + 108));
+                hm = ld_u32_a2(wb + 4 * L);
+                w = ld_u32_a2(wb + 32 + 32 * j + 4 * L);
+            }
+            p = 0;
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++) {
+                const int k = 2 * (part & 1) + kk, si = 8 * j + 2 * k + (L >= 4);
+                const uint32_t lo = (w >> (2 * k)) & 0x03030303u;
+                const int xw = *(const int *)(xb->qs + 128 * j + 32 * k + 4 * L);
+                if (TYPE == T_Q2_K) p += (int)(wb[si] & 0xF) * __dp4a((int)lo, xw, 0);
+                else {
+                    const uint32_t q3h = ((~(hm >> (4 * j + k))) & 0x01010101u) << 2;       // 4 where the high bit is NOT set (:1936-1948)
+                    const uint8_t *s = wb + 96;                                             // 6-bit scales, the aux[] shuffles of :1907-1913
+                    const int wd = si >> 2, c = si & 3;
+                    const int sc = (int)(((s[(wd & 1) * 4 + c] >> (4 * (wd >> 1))) & 0xF) | (((s[8 + c] >> (2 * wd)) & 3) << 4)) - 32;
+                    p += sc * (__dp4a((int)lo, xw, 0) - __dp4a((int)q3h, xw, 0));
+                }
+            }
+            p += __shfl_xor_sync(0xffffffffu, p, 8);
+            p += __shfl_xor_sync(0xffffffffu, p, 16);
+            acc = __fmaf_rn(d, (float)p, acc);
+        } else if (TYPE == T_Q6_K) {
             const float d = __fmul_rn(yd, h2f(wb + 208));
             const int j = part >> 1, hs = part & 1;
             const uint32_t wl = ld_u32_a2(wb + 64 * j + 32 * hs + 4 * L), wh = ld_u32_a2(wb + 128 + 32 * j + 4 * L);
@@ -150,7 +187,7 @@ __global__ void __launch_bounds__(128) mul_mat_kq_exact_kernel(const uint8_t *__
         accm = __fadd_rn(accm, __shfl_xor_sync(0xffffffffu, accm, 2));
         accm = __fadd_rn(accm, __shfl_xor_sync(0xffffffffu, accm, 1));
     }
-    if (TYPE != T_Q6_K) v = __fadd_rn(v, accm);
+    if (TYPE == T_Q4_K || TYPE == T_Q5_K) v = __fadd_rn(v, accm);
     if (lane == 0) dst[b * ldd + n] = addend ? __fadd_rn(v, addend[b * lda + n]) : v;
 }
 
@@ -174,6 +211,8 @@ void mul_mat_kq_exact(int type, const void *w_raw, const void *xq8k, float *dst,
     const dim3 grid((unsigned)((N + 3) / 4), (unsigned)B);
     const int64_t nsb = K / QKK;
     switch (type) {
+        case T_Q2_K: mul_mat_kq_exact_kernel<T_Q2_K><<<grid, 128, 0, st>>>((const uint8_t *)w_raw, (const BlockQ8K *)xq8k, dst, ldd, N, nsb, addend, lda); break;
+        case T_Q3_K: mul_mat_kq_exact_kernel<T_Q3_K><<<grid, 128, 0, st>>>((const uint8_t *)w_raw, (const BlockQ8K *)xq8k, dst, ldd, N, nsb, addend, lda); break;
         case T_Q4_K: mul_mat_kq_exact_kernel<T_Q4_K><<<grid, 128, 0, st>>>((const uint8_t *)w_raw, (const BlockQ8K *)xq8k, dst, ldd, N, nsb, addend, lda); break;
         case T_Q5_K: mul_mat_kq_exact_kernel<T_Q5_K><<<grid, 128, 0, st>>>((const uint8_t *)w_raw, (const BlockQ8K *)xq8k, dst, ldd, N, nsb, addend, lda); break;
         case T_Q6_K: mul_mat_kq_exact_kernel<T_Q6_K><<<grid, 128, 0, st>>>((const uint8_t *)w_raw, (const BlockQ8K *)xq8k, dst, ldd, N, nsb, addend, lda); break;

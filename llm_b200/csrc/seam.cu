@@ -191,7 +191,7 @@ void op_mul_mat(const ggml_tensor *src0, const ggml_tensor *src1, ggml_tensor *d
         return;
     }
     if (is_kquant(src0->type)) {
-        // Q4_K / Q5_K / Q6_K: the super-blocks stay in GGML's own layout (transform_tensor uploaded them as they are); quantize_row_q8_K + vec_dot order of the AVX2 build
+        // Q2_K .. Q6_K: the super-blocks stay in GGML's own layout (transform_tensor uploaded them as they are); quantize_row_q8_K + vec_dot order of the AVX2 build
         B200_ASSERT(src0->ne[2] == 1 && src0->ne[3] == 1 && is_contiguous(src0) && is_contiguous(dst));
         B200_ASSERT(src1->nb[0] == 4 && src1->ne[2] * src1->ne[3] == 1 || is_contiguous(src1));
         const int64_t K = src0->ne[0], N = src0->ne[1], B = nrows(src1);

@@ -894,7 +894,7 @@ int b200_op_quantize_q8_K(const float *x, int64_t K, int64_t B, void *blocks_out
     return B200_OK;
 }
 int b200_op_mul_mat(int32_t wtype, const void *w_ggml, int64_t K, int64_t N, const float *x, int64_t B, float *dst, int32_t impl) {
-    if (is_kquant(wtype)) {                              // Q4_K / Q5_K / Q6_K: one exact kernel (kquants.cu); `impl` must be AUTO or EXACT
+    if (is_kquant(wtype)) {                              // Q2_K .. Q6_K: one exact kernel (kquants.cu); `impl` must be AUTO or EXACT
         if (!w_ggml || !x || !dst || K % 256 || (impl != B200_MM_AUTO && impl != B200_MM_EXACT)) return B200_ERR_BAD_ARG;
         Runtime &R = rt(); R.ensure_init(); R.op_arena.reset();
         cudaStream_t st = R.stream;

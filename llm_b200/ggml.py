@@ -20,8 +20,8 @@ OP_RESHAPE, OP_VIEW, OP_PERMUTE, OP_TRANSPOSE, OP_GET_ROWS, OP_DIAG_MASK_INF, OP
 UNARY_GELU, UNARY_SILU = 7, 9
 TASK_INIT, TASK_COMPUTE, TASK_FINALIZE = 0, 1, 2
 BLOCK_BYTES = {Q4_0: 18, Q4_1: 20, Q5_0: 22, Q5_1: 24, Q8_0: 34, Q8_1: 40}
-Q4_K, Q5_K, Q6_K = 12, 13, 14                                  # K-quants served by the seam (256-element super-blocks, LC/k_quants.h:60-110)
-SUPER_BLOCK_BYTES = {Q4_K: 144, Q5_K: 176, Q6_K: 210}
+Q2_K, Q3_K, Q4_K, Q5_K, Q6_K = 10, 11, 12, 13, 14                  # K-quants served by the seam (256-element super-blocks, LC/k_quants.h:28-110)
+SUPER_BLOCK_BYTES = {Q2_K: 84, Q3_K: 110, Q4_K: 144, Q5_K: 176, Q6_K: 210}
 TYPE_SIZE = {F32: 4, F16: 2, I8: 1, I16: 2, I32: 4, **BLOCK_BYTES, **SUPER_BLOCK_BYTES}
 BLCK = {**{t: 32 for t in BLOCK_BYTES}, **{t: 256 for t in SUPER_BLOCK_BYTES}}
 

@@ -19,7 +19,7 @@ QUANT_TYPES = {"q4_0": Q4_0, "q4_1": Q4_1, "q5_0": Q5_0, "q5_1": Q5_1, "q8_0": Q
 # bytes per 32-element block (LC/ggml.c:895-940)
 BLOCK_BYTES = {Q4_0: 18, Q4_1: 20, Q5_0: 22, Q5_1: 24, Q8_0: 34, Q8_1: 40}
 Q2_K, Q3_K, Q4_K, Q5_K, Q6_K, Q8_K = 10, 11, 12, 13, 14, 15                    # LC/ggml.h:262-285; 256-element super-blocks (LC/k_quants.h)
-KQUANT_TYPES = {"q4_K": Q4_K, "q5_K": Q5_K, "q6_K": Q6_K}
+KQUANT_TYPES = {"q2_K": Q2_K, "q3_K": Q3_K, "q4_K": Q4_K, "q5_K": Q5_K, "q6_K": Q6_K}
 SUPER_BLOCK_BYTES = {Q2_K: 84, Q3_K: 110, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q8_K: 292}
 VEC_DOT_TYPE = {Q4_0: Q8_0, Q4_1: Q8_1, Q5_0: Q8_0, Q5_1: Q8_1, Q8_0: Q8_0}  # LC/ggml.c:1645-1737
 

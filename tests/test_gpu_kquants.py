@@ -1,5 +1,5 @@
-"""K-quant weights (Q4_K / Q5_K / Q6_K) through the C ABI, BIT-EXACT against the reference's own compiled k_quants.c (oracle/_ref):
-quantize_row_q8_K, ggml_vec_dot_q{4,5,6}_K_q8_K behind ggml_compute_forward_mul_mat, and the same node through the ggml_cuda_* seam."""
+"""K-quant weights (Q2_K .. Q6_K) through the C ABI, BIT-EXACT against the reference's own compiled k_quants.c (oracle/_ref):
+quantize_row_q8_K, ggml_vec_dot_q{2..6}_K_q8_K behind ggml_compute_forward_mul_mat, and the same node through the ggml_cuda_* seam."""
 import numpy as np
 import pytest
 

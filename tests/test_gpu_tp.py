@@ -84,7 +84,7 @@ TP_CFGS = {"mha": dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=8, n_layer=
            "gqa": dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=4, n_layer=2, n_ff=1024, n_rot=64, n_ctx=256)}
 
 
-@pytest.mark.parametrize("world,cfg,quant", [(2, "mha", "q4_0"), (2, "gqa", "q5_1"), (4, "mha", "q8_0")])
+@pytest.mark.parametrize("world,cfg,quant", [(2, "mha", "q4_0"), (2, "gqa", "q5_1"), (4, "mha", "q8_0"), (8, "mha", "q4_1")])
 def test_tensor_parallel_decode_bit_exact(tmp_path, world, cfg, quant):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
