@@ -380,7 +380,7 @@ def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
         line["exchange"] = {"per_token": 4 * hp["n_layer"] + 1, "gathered_bytes_per_token_per_gpu": exch, "nvlink_bytes_per_token_per_gpu_sent": exch * (world - 1) // world,
                             "ms_per_step_without_tag_waits": vals[2] / steps, "ms_per_step_local_stores_only": vals[3] / steps,
                             "exposed_wait_share_of_step": max(0.0, 1.0 - vals[2] / ms_dev), "peer_store_share_of_step": max(0.0, (vals[2] - vals[3]) / ms_dev),
-                            "relaxed_grid_waits": int(os.environ.get("B200_TP_RELAX", "1")),
+                            "relaxed_grid_waits": int(os.environ.get("B200_TP_RELAX", "0")),
                             "note": "same schedule with the tag waits skipped (garbage results) = compute + peer stores, and with every store kept local = compute alone; "
                                     "the differences are what waiting for the slowest rank's slices and what the NVLink stores cost"}
     emit(line)

@@ -556,7 +556,7 @@ static b200_session *start_session_tp(b200_session *s) {
     TpCtx &T = s->dp.tp;
     T = TpCtx();
     T.world = G; T.rank = r; T.vmul = (unsigned)hp.n_layer + 1;
-    { const char *e = getenv("B200_TP_RELAX"); T.relax = e ? atoi(e) : 1; }
+    { const char *e = getenv("B200_TP_RELAX"); T.relax = e ? atoi(e) : 0; }
     size_t off = 0;
     auto piece = [&](size_t units) { const size_t o = off; off += (units * 8 + 255) & ~(size_t)255; return (uint32_t)o; };
     T.off[TPB_X] = piece(e); T.off[TPB_FF] = piece(e); T.off[TPB_XD] = piece((e / QK) * 16); T.off[TPB_XF] = piece((f / QK) * 16); T.off[TPB_LOGITS] = piece(V);

@@ -31,10 +31,11 @@ struct TpCtx {                 // kernel argument (POD); world == 1: single GPU,
     unsigned vmul = 1;             // n_layer + 1
     int nowait = 0;                // measurement aid (b200_session_tp_set_nowait): 1 = accept whatever a unit holds -- results are garbage, the time is compute + stores;
                                    // 2 = additionally store to the local slab only: the time is compute alone
-    int relax = 1;                 // bit 0: the norm kernels, bit 1: the mat-vecs fed by exchanged records -- kernels whose every dependence on their predecessor
-                                   // travels through tagged units do not wait for the predecessor grid to COMPLETE (griddepcontrol.wait also waits for its
-                                   // peer stores to be acknowledged across NVLink).  Measured (profiles/r02_notes.md): 1 is best -- a relaxed mat-vec grid becomes
-                                   // resident early and its pollers take issue slots and L2 bandwidth from the producers.  B200_TP_RELAX overrides.
+    int relax = 0;                 // bit 0: the norm kernels, bit 1: the mat-vecs fed by exchanged records -- kernels whose every dependence on their predecessor
+                                   // travels through tagged units may skip griddepcontrol.wait (which also waits for the predecessor's peer stores to be
+                                   // acknowledged across NVLink).  Measured (profiles/r02_notes.md, r02l-r02o): compute alone falls from 1.86 to 1.42 ms / token (7B, 2 GPUs),
+                                   // but the early-resident pollers take issue slots and L2 bandwidth from the producers and the token gets no faster
+                                   // (2.02 / 2.09 / 2.09 ms for 0 / 1 / 3): default 0 = every kernel waits for its predecessor grid.  B200_TP_RELAX overrides.
 };
 
 // what one kernel instance reads / writes (baked into the CUDA graph; the epoch is read from device memory)
