@@ -249,7 +249,7 @@ BLK_BYTES = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
 
 def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
     """decode@1 at n_past = 512 of ONE model sharded by output rows over the N GPUs (strong scaling): every rank streams 1/N of the weights and its
-    heads' KV cache; activation slices cross NVLink as peer stores issued by the producing kernels' epilogues + release/acquire flags
+    heads' KV cache; activation slices cross NVLink as peer stores issued by the producing kernels' epilogues as tagged 8-byte units {payload, tag} the consumers poll locally
     (llm_b200/csrc/tp.cuh) -- torch.distributed (NCCL) only brackets the timed region and takes the max over ranks."""
     import llm_b200
     from llm_b200 import _lib, tp
@@ -365,7 +365,7 @@ def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
         "config": {"workload": f"{name} decode batch=1 n_past=512, ONE sequence on {world} GPU(s)" + (" (BASELINE.json configs[3])" if args.model == "13b-q5_1" else " (BASELINE.json configs[1])"),
                    "n_layer": hp["n_layer"], "n_ctx": 2048, "kv_cache": "f16",
                    "parallelism": (f"tp{world}: every weight matrix split by output rows (heads / n_ff / n_embd / n_vocab slices), bit-exact; activation slices are stored into every "
-                                   f"peer's buffers over NVLink by the producing epilogues + release/acquire flags; no NCCL on the data path") if world > 1 else "single GPU",
+                                   f"peer's buffers over NVLink by the producing epilogues as tagged 8-byte units (payload + tag, one 64-bit store) that the consumers poll locally; no collective, fence or flag on the data path") if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: weights streamed from HBM every step",
                    "weights": "random-init, generated on device, identical on every rank (same seed), each rank keeps its rows"},
         "e2e": {"value": steps / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * hp["n_vocab"] * world, "ms_per_step": ms_e2e / steps},

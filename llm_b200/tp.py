@@ -11,7 +11,7 @@ bit-identical to the single-GPU / CPU result:
     output                rows [r V/G, ...)
     tok_embeddings, norms whole on every rank
 torch.distributed carries only set-up traffic (the 64-byte CUDA IPC handles) and the barriers around timed regions; the per-token exchange is
-done by the decode kernels themselves (peer stores over NVLink + release/acquire flags).  Contrast: LC/ggml-cuda.cu:3355-3583."""
+done by the decode kernels themselves (peer stores over NVLink as tagged 8-byte units, polled locally by the consumers: tp.cuh).  Contrast: LC/ggml-cuda.cu:3355-3583."""
 import ctypes as C
 import os
 from typing import Dict
