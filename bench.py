@@ -88,6 +88,20 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    def hold(self, burst, agree=None, min_samples=2, max_s=4.0):
+        """Keep the SAME load running (untimed bursts) until nvidia-smi has reported at least `min_samples` rows: its start-up (0.1 - 0.6 s on an 8-GPU
+        box) can exceed a 64-token timed region, and a line without clocks is worthless.  `agree` = max over ranks, so every rank runs the same bursts."""
+        if not self.proc:
+            return
+        t0 = time.perf_counter()
+        while True:
+            need = 1.0 if (len(self.rows) < min_samples and time.perf_counter() - t0 < max_s) else 0.0
+            if agree is not None:
+                need = agree(need)
+            if need <= 0:
+                break
+            burst()
+
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
@@ -335,6 +349,12 @@ def tp_main(args, rank, local_rank, world, steps, warmup, emit, log):
             sess.rewind(N_PAST); L.b200_session_evaluate(sess._s, one.ctypes.data, 1, logits.ctypes.data, 0)
         ms_e2e = max(L.b200_timing_end_ms(), (time.perf_counter() - t0) * 1e3)
         barrier()
+
+        def burst():
+            for _ in range(32):
+                sess.rewind(N_PAST); L.b200_session_evaluate_device(sess._s, None, 1)
+            sess.sync()
+        clk.hold(burst, agree=(lambda v: allmax(v)[0]) if world > 1 else None)
     clocks = clk.summary()
     assert np.isfinite(logits).all()
     ms_nowait = ms_local = None
@@ -499,6 +519,10 @@ def main():
             L.b200_session_evaluate(sess._s, tok512.ctypes.data, N_PAST, last_row.ctypes.data, 0)
         pf_e2e = max(L.b200_timing_end_ms(), (time.perf_counter() - t0) * 1e3)
         barrier()
+
+        def pburst():
+            sess.rewind(0); L.b200_session_evaluate_device(sess._s, None, N_PAST); sess.sync()
+        pclk.hold(pburst)
     pf_clocks = pclk.summary()
     pf_dev, pf_e2e = allmax(pf_dev, pf_e2e)
     fl = prefill_flops(hp, N_PAST)
@@ -573,6 +597,12 @@ def main():
         # roofline probe of the dominant kernel (quantized mat-vec) on the real weights
         nl, nbytes = C.c_int64(0), C.c_double(0)
         ms_probe = L.b200_session_probe_matvec(sess._s, 3, C.byref(nl), C.byref(nbytes))
+
+        def burst():
+            for _ in range(32):
+                sess.rewind(N_PAST); L.b200_session_evaluate_device(sess._s, None, 1)
+            sess.sync()
+        clk.hold(burst)
     clocks = clk.summary()
     assert np.isfinite(logits).all()
     ms_dev, ms_e2e = allmax(ms_dev, ms_e2e)
