@@ -163,7 +163,9 @@ int32_t b200_session_last_launches(const b200_session *s);
 void b200_session_free(b200_session *s);
 /* Tensor-parallel sessions: each rank exports the CUDA IPC handle (64 bytes) of its exchange slab, the host layer gathers the handles of all ranks
  * (any channel: torch.distributed, MPI, a pipe) and hands the table [tp_world][64] back; after that the decode kernels store their output slices
- * straight into every peer's slab over NVLink (llm_b200/csrc/tp.cuh).  Every rank must call evaluate with the same tokens in the same order. */
+ * straight into every peer's slab over NVLink (llm_b200/csrc/tp.cuh).  Every rank must call evaluate with the same tokens in the same order.
+ * ONE tensor-parallel session per process: the exchange context (peer pointers, epoch) lives in constant memory of the decode kernels' module
+ * (one process per GPU, like the reference's one-session-per-process global state, LC/ggml-cuda.cu:2598-2686). */
 int  b200_session_tp_handle(b200_session *s, void *handle_out64);
 int  b200_session_tp_connect(b200_session *s, const void *handles_by_rank);
 int32_t b200_session_tp_timeouts(b200_session *s);
