@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call G (2 GPUs): tensor-parallel decode parity (world 2) and the TP bench lines for 7B Q4_0 and 13B Q5_1
+# round 2, call I (2 GPUs): the same two-rank parity + bench with the exchange rewritten as tagged 8-byte units
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader
 nvidia-smi topo -m 2>/dev/null | head -6

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call Q (1 GPU): driver-like validation (smoke, the whole GPU suite, default bench lines) + the ncu launch lists of the bench commands + v3b GEMM capture
+# round 2, call Q (1 GPU): driver-like validation (smoke, the whole GPU suite, default bench lines) + the ncu launch lists of the bench commands + v3b GEMM capture  [NOT RUN: the GPU budget of the round ended with call P; kept as the recipe for the next round]
 mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02q_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r02q_smoke.log
 ( timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider ) > gpurun_out/r02q_gpu_suite.log 2>&1; echo "gpu suite rc=$?"; tail -4 gpurun_out/r02q_gpu_suite.log | cut -c1-300
