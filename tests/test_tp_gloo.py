@@ -33,6 +33,30 @@ def test_row_split_rules_reassemble_and_match_the_oracle(orc):
         tp.shard_tensors(hp, tens, 0, 3)                    # 8 heads / 2 KV heads do not split three ways
 
 
+def test_row_split_at_4_and_8_ranks_and_published_geometries(orc):
+    """the same reassembly + exactness at 4 and 8 ranks (the multi-head test geometry of tests/test_gpu_tp.py), and the divisibility rule on the published
+    shapes: LLaMA-7B and 13B split 2 / 4 / 8 ways (whole heads, 32-row pieces of w1|w3 / wo / w2 / lm_head), not 3 or 16 ways"""
+    from llm_b200 import tp
+    cfg = dict(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=8, n_layer=1, n_ff=1024, n_rot=64, n_ctx=64)
+    hp, tens = synth.make_llama(cfg, B.Q4_0, orc.quantize)
+    x = np.random.default_rng(4).standard_normal((2, hp["n_embd"])).astype(np.float32)
+    for world in (4, 8):
+        shards = [tp.shard_tensors(hp, tens, r, world) for r in range(world)]
+        for name, full in tens.items():
+            assert np.array_equal(tp.unshard_rows(hp, name, [s[name] for s in shards]), full), (world, name)
+        for name in ("layers.0.feed_forward.w1.weight", "output.weight"):
+            whole = orc.mul_mat(B.Q4_0, tens[name], x)
+            parts = np.concatenate([orc.mul_mat(B.Q4_0, s[name], x) for s in shards], axis=1)
+            assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32)), (world, name)
+    for geom in ("7b", "13b"):
+        g = synth.CONFIGS[geom]
+        for world in (2, 4, 8):
+            tp.check_divisible(g, world)
+        for world in (3, 16):
+            with pytest.raises(ValueError):
+                tp.check_divisible(g, world)
+
+
 WORKER = textwrap.dedent('''
     import json, os, sys
     sys.path.insert(0, %r)
