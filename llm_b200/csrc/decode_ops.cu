@@ -78,8 +78,8 @@ __device__ __forceinline__ float f16dot_tree(float s) {          // ggml_vec_dot
 // ---- 1 / 6: rms_norm * gain -> records.  grid = e/128 CTAs of 256 threads; every CTA reduces the whole row (16 KB from L2) and
 //      quantizes its own 4 blocks per warp pass. ------------------------------------------------------------------------------------
 template <bool TP>
-__global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
-                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpSync S) {
+__device__ __forceinline__ void norm_pack_body(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
+                                               int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpSync &S) {
     const TpCtx &T = c_tp;
     __shared__ double shd[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,6 +139,16 @@ __global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict_
     pack_quad(v, pack + (active ? mine >> 3 : 0) * 4, lane, active, q81, off, scale16);
     prof_end(prof);
 }
+// Two entry points: the single-GPU kernel does not carry the 24 bytes of TpSync, so its argument block stays inside ONE 64-byte line of the constant bank
+// (56 B; with them, 80 B, the 4-CTA kernel measured +0.2..0.4 us per launch, 64 launches per token: profiles/r02m_timeline*.txt).
+__global__ void __launch_bounds__(256) norm_pack_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
+                                                        int e, float eps, int q81, int off, int scale16, unsigned long long *prof) {
+    norm_pack_body<false>(x, gain, pack, e, eps, q81, off, scale16, prof, TpSync{});
+}
+__global__ void __launch_bounds__(256) norm_pack_tp_kernel(const float *__restrict__ x, const float *__restrict__ gain, int4 *__restrict__ pack,
+                                                           int e, float eps, int q81, int off, int scale16, unsigned long long *prof, const TpSync S) {
+    norm_pack_body<true>(x, gain, pack, e, eps, q81, off, scale16, prof, S);
+}
 
 // ---- mat-vec with fused epilogues --------------------------------------------------------------------------------------------------
 enum { EPI_RES = 0, EPI_QKV = 1, EPI_SILU = 2, EPI_LOGITS = 3, EPI_BIAS = 4, EPI_GELU = 5 };   // BIAS / GELU: GPT-NeoX (bias adds, gelu table)
@@ -146,8 +156,14 @@ enum { EPI_RES = 0, EPI_QKV = 1, EPI_SILU = 2, EPI_LOGITS = 3, EPI_BIAS = 4, EPI
 struct MmvArgs {
     const int4 *xpack;            // input records
     float *dst; const float *addend;                       // EPI_RES / EPI_LOGITS
-    // EPI_QKV
-    float *q; __half *K, *V; const float2 *rope_cs; int rope_half, hd, e, gqa, n_ctx; const int *n_past;
+    // Two pointer groups that no launch uses together share their 32 bytes: the argument block (QWeight 72 B + this struct) then stays within four 64-byte
+    // lines of the constant bank (248 B; 280 B with both groups measured +0.2..0.4 us on every launch of the decode graph, profiles/r02_notes.md).
+    union {
+        struct { float *q; __half *K, *V; const float2 *rope_cs; };                            // EPI_QKV (LLaMA: RoPE + KV store)
+        // EPI_BIAS: dst = ((W x + bias) [+ add1]) [+ add2] in that order (ggml_add nodes of gptneox lib.rs:200,302,308-325); EPI_GELU: gelu(W x + bias) quantized
+        struct { const float *bias, *add1, *add2; const uint16_t *lut_gelu; };
+    };
+    int rope_half, hd, e, gqa, n_ctx; const int *n_past;                                      // EPI_QKV
     // EPI_SILU
     int4 *xpack_out; const uint16_t *lut_silu;
     int q81, off, scale16;
@@ -155,8 +171,6 @@ struct MmvArgs {
     int nst;                      // ring depth chosen by launch_mmv
     int pdl_early;                // trigger the dependents from the producer warp once every byte is requested (B200_PDL_EARLY, default 1)
     unsigned long long *prof;
-    // EPI_BIAS: dst = ((W x + bias) [+ add1]) [+ add2] in that order (ggml_add nodes of gptneox lib.rs:200,302,308-325); EPI_GELU: gelu(W x + bias) quantized
-    const float *bias, *add1, *add2; const uint16_t *lut_gelu;
     // tensor-parallel decode (tp.cuh): this rank owns rows [row0, row0 + w.N) of the full matrix; results go to buffer dst_buf of every rank
     TpSync ts; int64_t row0;
 };
@@ -644,6 +658,12 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     };
     int n = 0;
     auto pr = [&]() -> unsigned long long * { return P.prof && n < B200_PROF_SLOTS ? P.prof + n : nullptr; };   // timeline slot of the next launch
+    auto launch_norm = [&](const float *x, const float *gain, const TpSync &S) {               // rms_norm * gain -> records of the next mat-vec
+        const dim3 grid((e / QK + 31) / 32), block(256);
+        if constexpr (TP) launch_k(norm_pack_tp_kernel, grid, block, 0, st, x, gain, xpack_a, e, P.eps, q81, off, s16, pr(), S);
+        else { (void)S; launch_k(norm_pack_kernel, grid, block, 0, st, x, gain, xpack_a, e, P.eps, q81, off, s16, pr()); }
+        n++;
+    };
     get_rows_q(P.wte, P.token, P.x, 1, st); n++;
     if (tp) { launch_k(tp_spread_kernel, dim3((e + 255) / 256), dim3(256), 0, st, (const float *)P.x, e); n++; }
     // attention: one cluster launch per layer (default) or the two-kernel variant (B200_ATTN_FUSED=0, or head sizes a cluster cannot cover)
@@ -659,8 +679,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
     for (int il = 0; il < P.n_layer; il++) {
         const DecodeLayer &L = layers[il];
         const unsigned v = (unsigned)il + 1;                     // flag value of this layer's exchanges (tp.cuh)
-        launch_k(norm_pack_kernel<TP>, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, L.attn_norm, xpack_a, e, P.eps, q81, off, s16, pr(),
-                 ts(TPB_X, (unsigned)il, -1, 0, -1, 0)); n++;
+        launch_norm(P.x, L.attn_norm, ts(TPB_X, (unsigned)il, -1, 0, -1, 0));
         MmvArgs A{}; A.xpack = xpack_a; A.q = P.q; A.K = L.K; A.V = L.V; A.rope_cs = P.rope_cs; A.rope_half = P.rope_half; A.hd = P.hd; A.e = e_loc; A.gqa = P.gqa;
         A.n_ctx = P.n_ctx; A.n_past = P.n_past;
         A.prof = pr(); launch_mmv<TYPE, EPI_QKV, TP>(L.wqkv, A, st); n++;
@@ -687,7 +706,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
         MmvArgs Bo{}; Bo.xpack = P.xpack_d; Bo.dst = P.ff; Bo.addend = P.x;
         Bo.ts = ts(TPB_XD, v, TPB_X, (unsigned)il, TPB_FF, v); Bo.row0 = tp ? P.row0_e : 0;
         Bo.prof = pr(); launch_mmv<TYPE, EPI_RES, TP>(L.wo, Bo, st); n++;
-        launch_k(norm_pack_kernel<TP>, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.ff, L.ffn_norm, xpack_a, e, P.eps, q81, off, s16, pr(), ts(TPB_FF, v, -1, 0, -1, 0)); n++;
+        launch_norm(P.ff, L.ffn_norm, ts(TPB_FF, v, -1, 0, -1, 0));
         MmvArgs C{}; C.xpack = xpack_a; C.xpack_out = P.xpack_f; C.lut_silu = P.lut_silu; C.q81 = q81; C.off = off; C.scale16 = s16;
         C.ts = ts(-1, 0, -1, 0, TPB_XF, v); C.row0 = tp ? P.row0_w13 : 0;
         C.prof = pr(); launch_mmv<TYPE, EPI_SILU, TP>(L.w13, C, st); n++;
@@ -695,8 +714,7 @@ void decode_ops_t(const DecodeParams &P, const std::vector<DecodeLayer> &layers,
         D.ts = ts(TPB_XF, v, TPB_FF, v, TPB_X, v); D.row0 = tp ? P.row0_e : 0;
         D.prof = pr(); launch_mmv<TYPE, EPI_RES, TP>(L.w2, D, st); n++;
     }
-    launch_k(norm_pack_kernel<TP>, dim3((e / QK + 31) / 32), dim3(256), 0, st, P.x, P.norm, xpack_a, e, P.eps, q81, off, s16, pr(),
-             ts(TPB_X, (unsigned)P.n_layer, -1, 0, -1, 0)); n++;
+    launch_norm(P.x, P.norm, ts(TPB_X, (unsigned)P.n_layer, -1, 0, -1, 0));
     MmvArgs Z{}; Z.xpack = xpack_a; Z.dst = P.logits; Z.addend = nullptr; Z.n_past_inc = P.n_past;
     Z.ts = ts(-1, 0, -1, 0, TPB_LOGITS, 0); Z.row0 = tp ? P.row0_v : 0;
     Z.prof = pr(); launch_mmv<TYPE, EPI_LOGITS, TP>(P.output, Z, st); n++;
