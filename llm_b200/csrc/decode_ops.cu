@@ -174,6 +174,7 @@ struct MmvArgs {
     // tensor-parallel decode (tp.cuh): this rank owns rows [row0, row0 + w.N) of the full matrix; results go to buffer dst_buf of every rank
     TpSync ts; int64_t row0;
 };
+static_assert(sizeof(QWeight) + sizeof(MmvArgs) <= 256, "mat-vec argument block: at most four 64-byte lines of the constant bank (see the union above)");
 
 template <int TYPE, int EPI, bool TP>
 __global__ void __launch_bounds__(STHREADS) mmv_fused_kernel(const QWeight w, const MmvArgs A) {
